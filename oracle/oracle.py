@@ -1,0 +1,273 @@
+"""Python face of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Two independent restatements of the reference's `3dmpifft_opt` path live here:
+
+* `COracle`   -- ctypes binding of oracle_fft.c (own Stockham engine + the reference's stage
+                 index maps; multi-threaded; also the `cpu_baseline` / `--impl reference` arm).
+* `NumpySlab` -- the same stage boundaries written with numpy index arithmetic and numpy's
+                 pocketfft for the math.  It shares no code with oracle_fft.c, so agreement of
+                 the two (tests/test_oracle.py) checks both the engine and the layout maps.
+
+Layouts follow SURVEY.md Appendix A; reference citations are on each function
+(paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+FORWARD = 1    # 3dmpifft_opt/include/fft_mpi_common.h:18
+BACKWARD = -1  # fft_mpi_common.h:19
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle_fft.so")
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile oracle_fft.c with the committed Makefile (gcc is in the image)."""
+    src = os.path.join(_HERE, "oracle_fft.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "liboracle_fft.so"], check=True)
+    return _LIB
+
+
+def ceil_div(a: int, b: int) -> int:
+    return -(-a // b)
+
+
+@dataclass
+class SlabGeometry:
+    """Slab bookkeeping of fft_mpi_3d_api.cpp:56-66, 89-91 for P devices."""
+    n0: int
+    n1: int
+    n2: int
+    P: int
+
+    @property
+    def xd(self): return ceil_div(self.n0, self.P)
+    @property
+    def yd(self): return ceil_div(self.n1, self.P)
+    @property
+    def last_n0(self): return self.n0 - (self.P - 1) * self.xd
+    @property
+    def last_n1(self): return self.n1 - (self.P - 1) * self.yd
+    def n0l(self, p): return self.last_n0 if p == self.P - 1 else self.xd
+    def n1l(self, q): return self.last_n1 if q == self.P - 1 else self.yd
+
+    def max_count(self, p):
+        """getMaxDataCount, fft_mpi_3d_api.cpp:289-316"""
+        return max(self.n0l(p) * self.n1 * self.n2, self.n0 * self.n1l(p) * self.n2)
+
+    def in_count(self, p):
+        """getDataCountForNode, fft_mpi_3d_api.cpp:274-287"""
+        return self.n0l(p) * self.n1 * self.n2
+
+    def out_count(self, q):
+        return self.n0 * self.n1l(q) * self.n2
+
+
+def proper_device_num(n0: int, wanted: int) -> int:
+    """getProperDeviceNum, fft_mpi_3d_api.cpp:232-272 (single rank)."""
+    if n0 % wanted == 0:
+        return wanted
+    per = n0 // wanted + 1
+    dev = n0 // per
+    if n0 % per:
+        dev += 1
+    return dev
+
+
+# ------------------------------------------------------------------------------------------
+# numpy restatement (independent of oracle_fft.c)
+# ------------------------------------------------------------------------------------------
+class NumpySlab:
+    def __init__(self, n0, n1, n2, P):
+        self.g = SlabGeometry(n0, n1, n2, P)
+        if self.g.last_n0 < 1 or self.g.last_n1 < 1:
+            raise ValueError("empty last slab")
+
+    # -- helpers ---------------------------------------------------------------------------
+    def scatter_input(self, A):
+        """global A[x][y][z] -> per-device buf1 (flat, max_count long)"""
+        g = self.g
+        out = []
+        for p in range(g.P):
+            b = np.zeros(g.max_count(p), dtype=A.dtype)
+            sl = A[p * g.xd: p * g.xd + g.n0l(p)].reshape(-1)
+            b[: sl.size] = sl
+            out.append(b)
+        return out
+
+    def gather_forward_output(self, buf2):
+        """per-device [y_l][z][x] -> global spectrum S[x][y][z]"""
+        g = self.g
+        S = np.empty((g.n0, g.n1, g.n2), dtype=buf2[0].dtype)
+        for q in range(g.P):
+            blk = buf2[q][: g.out_count(q)].reshape(g.n1l(q), g.n2, g.n0)
+            S[:, q * g.yd: q * g.yd + g.n1l(q), :] = blk.transpose(2, 0, 1)
+        return S
+
+    def gather_natural(self, bufs):
+        g = self.g
+        return np.concatenate([bufs[p][: g.in_count(p)] for p in range(g.P)]).reshape(g.n0, g.n1, g.n2)
+
+    # -- stages ----------------------------------------------------------------------------
+    def t0(self, buf, p, direction):
+        """fftZY, fft_mpi_3d_api.cpp:466-522: in-place 2-D transform of each local plane."""
+        g = self.g
+        v = buf[: g.in_count(p)].reshape(g.n0l(p), g.n1, g.n2)
+        f = np.fft.fft2 if direction == FORWARD else (lambda a, axes: np.fft.ifft2(a, axes=axes) * (g.n1 * g.n2))
+        buf[: g.in_count(p)] = f(v, axes=(1, 2)).reshape(-1)
+
+    def pack_index(self, p):
+        """kernel_func.cpp:73-86: packed position of every natural element of device p."""
+        g = self.g
+        xs = g.n0l(p)
+        x, y, z = np.meshgrid(np.arange(xs), np.arange(g.n1), np.arange(g.n2), indexing="ij")
+        q = y // g.yd
+        w = np.where(q == g.P - 1, g.last_n1, g.yd)
+        return (xs * g.yd * g.n2 * q + x * w * g.n2 + (y % g.yd) * g.n2 + z).reshape(-1)
+
+    def t1(self, src, dst, p, direction):
+        idx = self.pack_index(p)
+        n = idx.size
+        if direction == FORWARD:
+            dst[idx] = src[:n]
+        else:
+            dst[:n] = src[idx]
+
+    def t2(self, buf2, buf1, direction):
+        """slabAlltoall, fft_mpi_3d_api.cpp:610-672 with the tables of :84-133."""
+        g = self.g
+        for s in range(g.P):
+            for i in range(g.P):
+                if direction == FORWARD:
+                    cnt = g.n0l(s) * g.n1l(i) * g.n2
+                    soff = i * g.n0l(s) * g.yd * g.n2
+                    roff = s * g.xd * g.n1l(i) * g.n2
+                else:
+                    cnt = g.n0l(i) * g.n1l(s) * g.n2
+                    soff = i * g.xd * g.n1l(s) * g.n2
+                    roff = s * g.n0l(i) * g.yd * g.n2
+                buf1[i][roff: roff + cnt] = buf2[s][soff: soff + cnt]
+
+    def t3(self, buf1, buf2, q, direction):
+        """fftX, fft_mpi_3d_api.cpp:524-573 (+ kernels_201.cpp:46-57 / kernels_120.cpp:45-57)."""
+        g = self.g
+        n = g.out_count(q)
+        if direction == FORWARD:
+            v = buf1[:n].reshape(g.n0, g.n1l(q), g.n2).transpose(1, 2, 0)
+            buf2[:n] = np.fft.fft(v, axis=2).reshape(-1)
+        else:
+            v = np.fft.ifft(buf1[:n].reshape(g.n1l(q), g.n2, g.n0), axis=2) * g.n0
+            buf1[:n] = v.reshape(-1)  # the reference transforms bufferDev1 in place (api.cpp:561)
+            buf2[:n] = v.transpose(2, 0, 1).reshape(-1)
+
+    def execute(self, buf1, buf2, direction, stop_after=3):
+        """fft_mpi_execute_dft_3d_c2c, fft_mpi_3d_api.cpp:181-214."""
+        g = self.g
+        if direction == FORWARD:
+            for p in range(g.P): self.t0(buf1[p], p, direction)
+            if stop_after == 0: return
+            for p in range(g.P): self.t1(buf1[p], buf2[p], p, direction)
+            if stop_after == 1: return
+            self.t2(buf2, buf1, direction)
+            if stop_after == 2: return
+            for q in range(g.P): self.t3(buf1[q], buf2[q], q, direction)
+        else:
+            for q in range(g.P): self.t3(buf1[q], buf2[q], q, direction)
+            if stop_after == 0: return
+            self.t2(buf2, buf1, direction)
+            if stop_after == 1: return
+            for p in range(g.P): self.t1(buf1[p], buf2[p], p, direction)
+            if stop_after == 2: return
+            for p in range(g.P): self.t0(buf2[p], p, direction)
+
+
+# ------------------------------------------------------------------------------------------
+# ctypes binding of oracle_fft.c
+# ------------------------------------------------------------------------------------------
+class COracle:
+    def __init__(self):
+        self.lib = ctypes.CDLL(build_oracle())
+        L = self.lib
+        i64 = ctypes.c_longlong
+        vp = ctypes.c_void_p
+        L.oracle_radix_schedule.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.oracle_radix_schedule.restype = ctypes.c_int
+        L.oracle_fft_batch.argtypes = [vp, ctypes.c_int, i64, i64, i64, i64, i64, ctypes.c_int]
+        L.oracle_fft_batch.restype = None
+        L.oracle_proper_device_num.argtypes = [i64, ctypes.c_int]
+        L.oracle_proper_device_num.restype = ctypes.c_int
+        L.oracle_max_data_count.argtypes = [i64, i64, i64, ctypes.c_int, ctypes.c_int]
+        L.oracle_max_data_count.restype = i64
+        L.oracle_exchange_table.argtypes = [i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+        L.oracle_exchange_table.restype = None
+        L.oracle_slab_execute.argtypes = [ctypes.c_int, i64, i64, i64, vp, vp, ctypes.c_int, ctypes.c_int]
+        L.oracle_slab_execute.restype = ctypes.c_int
+        L.oracle_fill_ramp.argtypes = [vp, i64, i64]
+        L.oracle_fill_minstd.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_ulonglong)]
+        L.oracle_roundtrip_error.argtypes = [vp, vp, i64, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+        L.oracle_roundtrip_error.restype = ctypes.c_double
+        L.oracle_num_threads.restype = ctypes.c_int
+
+    def radix_schedule(self, n):
+        r = (ctypes.c_int * 32)()
+        k = self.lib.oracle_radix_schedule(n, r)
+        return list(r[:k])
+
+    def num_threads(self):
+        return int(self.lib.oracle_num_threads())
+
+    def fft_axis(self, a: np.ndarray, axis: int, sign: int) -> np.ndarray:
+        """1-D transforms along `axis` of a C-contiguous complex128 array (copy returned)."""
+        a = np.ascontiguousarray(a, dtype=np.complex128).copy()
+        n = a.shape[axis]
+        stride = int(np.prod(a.shape[axis + 1:], dtype=np.int64))
+        outer = int(np.prod(a.shape[:axis], dtype=np.int64))
+        self.lib.oracle_fft_batch(a.ctypes.data, n, stride, outer * stride, stride, 1, n * stride, sign)
+        return a
+
+    def exchange_table(self, n0, n1, n2, P, dev, direction):
+        arrs = [np.zeros(P, dtype=np.int64) for _ in range(4)]
+        self.lib.oracle_exchange_table(n0, n1, n2, P, dev, direction, *[a.ctypes.data for a in arrs])
+        return dict(zip(("scount", "soffset", "rcount", "roffset"), arrs))
+
+    def slab_execute(self, geom: SlabGeometry, buf1, buf2, direction, stop_after=3):
+        P = geom.P
+        p1 = (ctypes.c_void_p * P)(*[b.ctypes.data for b in buf1])
+        p2 = (ctypes.c_void_p * P)(*[b.ctypes.data for b in buf2])
+        rc = self.lib.oracle_slab_execute(P, geom.n0, geom.n1, geom.n2, p1, p2, direction, stop_after)
+        if rc != 0:
+            raise ValueError("oracle_slab_execute failed (empty last slab?)")
+
+    def fill_ramp(self, dst: np.ndarray, start: int):
+        self.lib.oracle_fill_ramp(dst.ctypes.data, start, dst.size)
+
+    def fill_minstd(self, dst: np.ndarray, state: int = 4242) -> int:
+        st = ctypes.c_ulonglong(state)
+        self.lib.oracle_fill_minstd(dst.ctypes.data, dst.size, ctypes.byref(st))
+        return int(st.value)
+
+    def roundtrip_error(self, a: np.ndarray, b: np.ndarray, n3: float):
+        ab = ctypes.c_double(0)
+        drv = self.lib.oracle_roundtrip_error(a.ctypes.data, b.ctypes.data, a.size, float(n3), ctypes.byref(ab))
+        return float(drv), float(ab.value)
+
+
+def minstd_uniform(count: int, state: int = 4242):
+    """numpy restatement of heffte/heffteBenchmark/test/test_fft3d.h:19-27 input
+    (std::minstd_rand(4242) -> uniform_real_distribution<double>(0,1)); returns (values, state)."""
+    a, m = 48271, 2147483647
+    R = float(m - 1)
+    out = np.empty(count, dtype=np.float64)
+    s = state
+    for j in range(count):
+        s = (s * a) % m; lo = s - 1
+        s = (s * a) % m; hi = s - 1
+        out[j] = (lo + hi * R) / (R * R)
+    return out, s
