@@ -398,14 +398,14 @@ void oracle_fill_ramp(cplx *dst, i64 start, i64 count)
 void oracle_fill_minstd(cplx *dst, i64 count, unsigned long long *state)
 {
     const unsigned long long a = 48271ULL, m = 2147483647ULL;
-    const long double R = 2147483646.0L;
+    const double R = 2147483646.0; /* urng.max() - urng.min() + 1, arithmetic in double like libstdc++ */
     unsigned long long s = *state;
     for (i64 j = 0; j < count; j++) {
-        s = (s * a) % m; long double lo = (long double)(s - 1);
-        s = (s * a) % m; long double hi = (long double)(s - 1);
-        long double v = (lo + hi * R) / (R * R);
-        if (v >= 1.0L) v = nextafterl(1.0L, 0.0L);
-        dst[j].re = (double)v; dst[j].im = 0.0;
+        s = (s * a) % m; double lo = (double)(s - 1);
+        s = (s * a) % m; double hi = (double)(s - 1);
+        double v = (lo + hi * R) / (R * R);
+        if (v >= 1.0) v = nextafter(1.0, 0.0);
+        dst[j].re = v; dst[j].im = 0.0;
     }
     *state = s;
 }
