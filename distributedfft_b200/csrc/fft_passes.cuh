@@ -1,0 +1,211 @@
+// fft_passes.cuh -- the one tile kernel all passes instantiate.
+//
+// A "tile" is C lines of N points.  Addressing is affine with an optional chunk table:
+//   element (tile, c, e) lives at  base + a*SA + b*SB + c*cs + e*es,  (a, b) = (tile / G, tile % G)
+// which covers
+//   Z pass  (t0, contiguous lines)          cs = N2, es = 1          thread map MAP_T
+//   Y pass  (t0, stride N2, +fused t1 pack) cs = 1,  es = N2         thread map MAP_C
+//   X pass  (t3, fused unpack + transpose)  load cs = 1, es = n1_l*N2 (MAP_C); store cs = N0, es = 1 (MAP_T)
+// and their backward twins.  With CHUNK_* the position e is split as q = e / ediv, el = e % ediv
+// and the address becomes  cptr[q] + a*SAq[q] + b*SB + c*cs + el*es : that is the reference's
+// per-destination pack (kernel_func.cpp:73-86) folded into the Y-pass store, with cptr[q] either
+// the local send buffer chunk or -- fused all-to-all -- the peer's receive buffer mapped over
+// NVLink (fft_mpi_3d_api.cpp:613-630 hipMemcpyPeerAsync into nodeDataDev[i]).
+#pragma once
+#include "fft_core.cuh"
+
+namespace dfft {
+
+enum { MAP_T = 0, MAP_C = 1 };
+constexpr int DFFT_MAX_CHUNKS = 32;
+
+struct Affine {
+    long long SA, SB, cs, es;
+};
+
+struct ChunkTab {
+    void* cptr[DFFT_MAX_CHUNKS];        // base pointer of chunk q (already includes the fixed offset)
+    long long SAq[DFFT_MAX_CHUNKS];     // stride of tile coordinate `a` inside chunk q
+    int ediv;                           // chunk extent along the transform axis (yd or xd)
+    int nchunks;
+};
+
+template <typename T> struct TileArgs {
+    const cx<T>* in;
+    cx<T>* out;
+    const cx<T>* lut;      // per-length twiddle table (Sched::lut_size() entries)
+    Affine ia, oa;
+    long long ntiles;      // total tiles
+    int G;                 // tiles per `a`
+    int W;                 // columns per `a` (for the ragged last tile: valid = min(C, W - b*C))
+    T scale;               // applied on store when SCALE
+    ChunkTab ci, co;       // used when CHUNK_IN / CHUNK_OUT
+};
+
+template <class S, typename T, int C, bool PINGPONG>
+struct TileSmem {
+    static constexpr int LS = SmemGeom<T>::line(S::N, C);
+    static constexpr size_t exch_bytes = (S::NSTAGES > 1 ? (PINGPONG ? 2 : 1) : 0) * (size_t)C * LS * sizeof(cx<T>);
+    static constexpr size_t lut_bytes = (size_t)((S::lut_size() * sizeof(cx<T>) + 15) / 16 * 16);
+    static constexpr size_t tab_bytes = (size_t)S::N * sizeof(int2) * 2 + 2 * DFFT_MAX_CHUNKS * 16;
+    static constexpr size_t bytes(bool chunked) { return exch_bytes + lut_bytes + 16 + (chunked ? tab_bytes : 0); }
+};
+
+template <class S, int s, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool PINGPONG>
+struct StageRunner {
+    static constexpr int LAST = S::NSTAGES - 1;
+    static constexpr int LS = SmemGeom<T>::line(S::N, C);
+    // thread (t_in, c_in) for every stage but the last, (t_out, c_out) for the last one
+    static __device__ __forceinline__ void run(cx<T>* v, int t_in, int c_in, int t_out, int c_out, cx<T>* exch,
+                                               int& pp, const cx<T>* lut, const cx<T>* twr)
+    {
+        const int t = (s == LAST) ? t_out : t_in;
+        stage_compute<S, s, T, TWREG>(v, t, lut, twr);
+        if constexpr (s < LAST) {
+            cx<T>* buf = exch + (PINGPONG ? (size_t)pp * C * LS : 0);
+            if constexpr (!PINGPONG) __syncthreads();   // previous readers of the single buffer are done
+            stage_scatter<S, s, T>(v, t_in, buf + c_in * LS);
+            __syncthreads();
+            if constexpr (s + 1 == LAST) stage_gather<S, T>(v, t_out, buf + c_out * LS);
+            else stage_gather<S, T>(v, t_in, buf + c_in * LS);
+            pp ^= 1;
+            StageRunner<S, s + 1, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, exch, pp, lut,
+                                                                    twr + S::tw_regs(s));
+        }
+    }
+};
+
+template <class S, int s, typename T> struct TwLoader {
+    static __device__ __forceinline__ void run(cx<T>* twr, int t_in, int t_out, const cx<T>* lut)
+    {
+        if constexpr (s < S::NSTAGES) {
+            if constexpr (s > 0) stage_load_tw<S, s, T>(twr, s == S::NSTAGES - 1 ? t_out : t_in, lut);
+            TwLoader<S, s + 1, T>::run(twr + S::tw_regs(s), t_in, t_out, lut);
+        }
+    }
+};
+
+template <int MAP, int C, int TT> __device__ __forceinline__ void thread_map(int tid, int& t, int& c)
+{
+    if constexpr (MAP == MAP_T) { t = tid % TT; c = tid / TT; }
+    else { c = tid % C; t = tid / C; }
+}
+
+// streaming accesses: every element is touched exactly once per pass, so keep it out of L1
+template <typename C_> __device__ __forceinline__ C_ ld_stream(const C_* p) { return __ldcg(p); }
+template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { __stcg(p, v); }
+
+template <class S, typename T, int C, int MAPIN, int MAPOUT, bool INV, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT,
+          bool PREFETCH, bool SCALE, int MINB, bool PINGPONG = true>
+__global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<T> A)
+{
+    static_assert(S::valid(), "bad schedule");
+    using SM = TileSmem<S, T, C, PINGPONG>;
+    constexpr int R = S::R, TT = S::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* exch = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* lut_s = reinterpret_cast<cx<T>*>(smem_raw + SM::exch_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::exch_bytes + SM::lut_bytes);
+    unsigned char* tabs = smem_raw + SM::exch_bytes + SM::lut_bytes + 16;
+    int2* etab_i = reinterpret_cast<int2*>(tabs);
+    int2* etab_o = etab_i + S::N;
+    char** cptr_i = reinterpret_cast<char**>(etab_o + S::N);
+    char** cptr_o = cptr_i + DFFT_MAX_CHUNKS;
+    long long* saq_i = reinterpret_cast<long long*>(cptr_o + DFFT_MAX_CHUNKS);
+    long long* saq_o = saq_i + DFFT_MAX_CHUNKS;
+
+    const int tid = threadIdx.x;
+    int t_in, c_in, t_out, c_out;
+    thread_map<MAPIN, C, TT>(tid, t_in, c_in);
+    thread_map<MAPOUT, C, TT>(tid, t_out, c_out);
+
+    // twiddle tile: global -> shared by one TMA bulk copy
+    stage_twiddles_tma<T>(lut_s, A.lut, S::lut_size(), bar);
+    if constexpr (CHUNK_IN || CHUNK_OUT) {
+        for (int e = tid; e < S::N; e += TT * C) {
+            if (CHUNK_IN) { int q = e / A.ci.ediv; q = q < A.ci.nchunks ? q : A.ci.nchunks - 1; etab_i[e] = make_int2(q, e - q * A.ci.ediv); }
+            if (CHUNK_OUT) { int q = e / A.co.ediv; q = q < A.co.nchunks ? q : A.co.nchunks - 1; etab_o[e] = make_int2(q, e - q * A.co.ediv); }
+        }
+        if (tid < DFFT_MAX_CHUNKS) {
+            if (CHUNK_IN) { cptr_i[tid] = (char*)A.ci.cptr[tid]; saq_i[tid] = A.ci.SAq[tid]; }
+            if (CHUNK_OUT) { cptr_o[tid] = (char*)A.co.cptr[tid]; saq_o[tid] = A.co.SAq[tid]; }
+        }
+        __syncthreads();
+    }
+
+    cx<T> twr[TWREG ? (S::tw_regs_total() > 0 ? S::tw_regs_total() : 1) : 1];
+    if constexpr (TWREG) TwLoader<S, 0, T>::run(twr, t_in, t_out, lut_s);
+
+    auto load_tile = [&](cx<T>* v, long long tile) {
+        const long long a = tile / A.G;
+        const int b = (int)(tile - a * A.G);
+        const bool ok = b * C + c_in < A.W;
+        if constexpr (!CHUNK_IN) {
+            const cx<T>* p = A.in + a * A.ia.SA + b * A.ia.SB + c_in * A.ia.cs + (long long)t_in * A.ia.es;
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                cx<T> x = ok ? ld_stream(p + (long long)u * TT * A.ia.es) : mk<T>(0, 0);
+                v[u] = INV ? cswap(x) : x;
+            }
+        } else {
+            const long long off = b * A.ia.SB + c_in * A.ia.cs;
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int2 qe = etab_i[t_in + u * TT];
+                const cx<T>* p = reinterpret_cast<const cx<T>*>(cptr_i[qe.x]) + a * saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
+                cx<T> x = ok ? ld_stream(p) : mk<T>(0, 0);
+                v[u] = INV ? cswap(x) : x;
+            }
+        }
+    };
+    auto store_tile = [&](const cx<T>* v, long long tile) {
+        const long long a = tile / A.G;
+        const int b = (int)(tile - a * A.G);
+        const bool ok = b * C + c_out < A.W;
+        if (!ok) return;
+        if constexpr (!CHUNK_OUT) {
+            cx<T>* p = A.out + a * A.oa.SA + b * A.oa.SB + c_out * A.oa.cs + (long long)t_out * A.oa.es;
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                cx<T> x = INV ? cswap(v[u]) : v[u];
+                if constexpr (SCALE) { x.x *= A.scale; x.y *= A.scale; }
+                st_stream(p + (long long)u * TT * A.oa.es, x);
+            }
+        } else {
+            const long long off = b * A.oa.SB + c_out * A.oa.cs;
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int2 qe = etab_o[t_out + u * TT];
+                cx<T>* p = reinterpret_cast<cx<T>*>(cptr_o[qe.x]) + a * saq_o[qe.x] + off + (long long)qe.y * A.oa.es;
+                cx<T> x = INV ? cswap(v[u]) : v[u];
+                if constexpr (SCALE) { x.x *= A.scale; x.y *= A.scale; }
+                st_stream(p, x);
+            }
+        }
+    };
+
+    int pp = 0;
+    long long tile = blockIdx.x;
+    cx<T> cur[R];
+    if constexpr (PREFETCH) {
+        if (tile < A.ntiles) load_tile(cur, tile);
+    }
+    while (tile < A.ntiles) {
+        const long long next = tile + gridDim.x;
+        cx<T> nxt[PREFETCH ? R : 1];
+        if constexpr (PREFETCH) {
+            if (next < A.ntiles) load_tile(nxt, next);
+        } else {
+            load_tile(cur, tile);
+        }
+        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(cur, t_in, c_in, t_out, c_out, exch, pp, lut_s, twr);
+        store_tile(cur, tile);
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int u = 0; u < R; u++) cur[u] = nxt[u];
+        }
+        tile = next;
+    }
+}
+
+}  // namespace dfft
