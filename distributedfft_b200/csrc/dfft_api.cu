@@ -1,0 +1,904 @@
+// dfft_api.cu -- C-ABI implementation: slab bookkeeping, communicator, plan, stage sequencing.
+//
+// Host-side counterpart of 3dmpifft_opt/include/fft_mpi_3d_api.cpp (plan :41-141, execute :181-214,
+// stages :466-699) re-designed for B200: three batched pass launches per transform instead of two
+// launches per plane, the pack folded into the Y-pass store, the all-to-all either fused into that
+// store over NVLink peer mappings or handed to NCCL, CUDA events instead of host timers, explicit
+// streams and no device-wide syncs on the production path.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dfft.h"
+#include "dfft_kernels.cuh"
+
+using namespace dfft;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    if (getenv("DFFT_VERBOSE")) fprintf(stderr, "[dfft] error %d: %s\n", code, buf);
+    return code;
+}
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return fail(DFFT_ECUDA, "%s:%d CUDA call '%s' failed: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* dfft_last_error(void) { return g_err.c_str(); }
+extern "C" int dfft_version(void) { return 100; }
+
+extern "C" int dfft_supported_lengths(int precision, int* lengths, int max_lengths)
+{
+    std::vector<int> v;
+    list_sizes(precision, v);
+    std::sort(v.begin(), v.end());
+    if (lengths)
+        for (int i = 0; i < (int)v.size() && i < max_lengths; i++) lengths[i] = v[i];
+    return (int)v.size();
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab geometry (fft_mpi_3d_api.cpp:56-66, 89-91, 232-316)
+// ------------------------------------------------------------------------------------------------
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+struct Geom {
+    long long n0, n1, n2;
+    int P;
+    long long xd() const { return cdiv(n0, P); }
+    long long yd() const { return cdiv(n1, P); }
+    long long last_n0() const { return n0 - (P - 1) * xd(); }
+    long long last_n1() const { return n1 - (P - 1) * yd(); }
+    long long n0l(int p) const { return p == P - 1 ? last_n0() : xd(); }
+    long long n1l(int q) const { return q == P - 1 ? last_n1() : yd(); }
+    long long in_count(int p) const { return n0l(p) * n1 * n2; }
+    long long out_count(int q) const { return n0 * n1l(q) * n2; }
+    long long max_count(int p) const { return std::max(in_count(p), out_count(p)); }
+};
+
+static int proper_device_num(long long n0, int wanted)
+{
+    if (wanted < 1) return 0;
+    if (n0 % wanted == 0) return wanted;
+    long long per = n0 / wanted + 1;
+    int dev = (int)(n0 / per);
+    if (n0 % per) dev += 1;
+    return dev;
+}
+
+extern "C" int dfft_init(const long long N[3], int wanted, int* total, int* local, long long* counts)
+{
+    if (!N || wanted < 1 || N[0] < 1 || N[1] < 1 || N[2] < 1) return fail(DFFT_EINVAL, "dfft_init: bad arguments");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+    if (ndev > 0 && wanted > ndev) wanted = ndev;   // api.cpp:236-239
+    int dev = proper_device_num(N[0], wanted);
+    if (dev < 1) return fail(DFFT_EUNSUPPORTED, "could not support this distribution of data");
+    Geom g{N[0], N[1], N[2], dev};
+    if (g.last_n1() < 1) return fail(DFFT_EUNSUPPORTED, "N1=%lld cannot be split over %d devices (empty last y-slab)", N[1], dev);
+    if (counts)
+        for (int i = 0; i < dev; i++) counts[i] = g.in_count(i);
+    if (total) *total = dev;
+    if (local) *local = dev;
+    // peer access between the devices used (api.cpp:16-27)
+    for (int i = 0; i < dev && i < ndev; i++) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cudaSetDevice(i) != cudaSuccess) { cudaGetLastError(); continue; }
+        for (int j = 0; j < dev && j < ndev; j++) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, i, j) == cudaSuccess && can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(j, 0);
+                if (pe != cudaSuccess) cudaGetLastError();   // already enabled is fine
+            }
+        }
+        cudaSetDevice(cur);
+    }
+    return 0;
+}
+
+extern "C" long long dfft_max_data_count(long long n0, long long n1, long long n2, int P, int is_last)
+{
+    if (P < 1) return -1;
+    Geom g{n0, n1, n2, P};
+    return g.max_count(is_last ? P - 1 : 0);
+}
+
+extern "C" long long dfft_local_size_3d(long long n0, long long n1, long long n2, int P, int dev, long long* ln0,
+                                        long long* s0, long long* ln1, long long* s1)
+{
+    if (P < 1 || dev < 0 || dev >= P) return -1;
+    Geom g{n0, n1, n2, P};
+    if (ln0) *ln0 = g.n0l(dev);
+    if (s0) *s0 = dev * g.xd();
+    if (ln1) *ln1 = g.n1l(dev);
+    if (s1) *s1 = dev * g.yd();
+    return g.max_count(dev);
+}
+
+extern "C" void* dfft_alloc_local(long long count, int flag, int precision)
+{
+    if (count < 0) { fail(DFFT_EINVAL, "negative count"); return nullptr; }
+    size_t bytes = (size_t)count * (precision == DFFT_FLOAT ? 8 : 16);
+    if (bytes == 0) bytes = 16;
+    void* p = nullptr;
+    cudaError_t e;
+    if (flag == DFFT_ALLOC_CPU) e = cudaMallocHost(&p, bytes);
+    else if (flag == DFFT_ALLOC_DEV) e = cudaMalloc(&p, bytes);
+    else { fail(DFFT_EINVAL, "Fail to allocate memory!"); return nullptr; }
+    if (e != cudaSuccess) { fail(DFFT_ENOMEM, "allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" int dfft_free_local(void* p, int flag)
+{
+    if (!p) return 0;
+    if (flag == DFFT_ALLOC_CPU) CU(cudaFreeHost(p));
+    else CU(cudaFree(p));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// communicator
+// ------------------------------------------------------------------------------------------------
+struct dfft_comm_s {
+    int nranks = 1;
+    bool local = true;
+    // local (threads of one process)
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    long long gen = 0;
+    std::vector<std::vector<unsigned char>> slots;
+    // bootstrap (process per GPU)
+    int rank = 0;
+    dfft_allgather_fn ag = nullptr;
+    void* ctx = nullptr;
+
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        long long g = gen;
+        if (++arrived == nranks) { arrived = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+    int allgather(int r, const void* send, void* recv, size_t bytes)
+    {
+        if (nranks == 1) { memcpy(recv, send, bytes); return 0; }
+        if (!local) return ag(ctx, send, recv, bytes);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            slots[r].assign((const unsigned char*)send, (const unsigned char*)send + bytes);
+        }
+        barrier();
+        for (int i = 0; i < nranks; i++) memcpy((unsigned char*)recv + (size_t)i * bytes, slots[i].data(), bytes);
+        barrier();
+        return 0;
+    }
+    int host_barrier(int r)
+    {
+        if (nranks == 1) return 0;
+        if (local) { barrier(); return 0; }
+        std::vector<unsigned char> tmp(nranks);
+        unsigned char one = 1;
+        return ag(ctx, &one, tmp.data(), 1);
+    }
+};
+
+extern "C" int dfft_comm_create_local(int nranks, dfft_comm* comm)
+{
+    if (nranks < 1 || !comm) return fail(DFFT_EINVAL, "dfft_comm_create_local: bad arguments");
+    dfft_comm c = new dfft_comm_s;
+    c->nranks = nranks;
+    c->local = true;
+    c->slots.resize(nranks);
+    *comm = c;
+    return 0;
+}
+
+extern "C" int dfft_comm_create_bootstrap(int rank, int nranks, dfft_allgather_fn ag, void* ctx, dfft_comm* comm)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks || !comm || (nranks > 1 && !ag))
+        return fail(DFFT_EINVAL, "dfft_comm_create_bootstrap: bad arguments");
+    dfft_comm c = new dfft_comm_s;
+    c->nranks = nranks;
+    c->local = false;
+    c->rank = rank;
+    c->ag = ag;
+    c->ctx = ctx;
+    *comm = c;
+    return 0;
+}
+
+extern "C" int dfft_comm_destroy(dfft_comm c)
+{
+    delete c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded at run time (no link-time dependency; picks up the copy torch already loaded)
+// ------------------------------------------------------------------------------------------------
+struct NcclUid { char b[128]; };   // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AlltoAll)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;   // NCCL >= 2.28
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    bool ok = false;
+};
+
+static NcclApi& nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("DFFT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n) continue;
+            api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.h) break;
+        }
+        if (!api.h) return;
+#define LD(field, sym) *(void**)(&api.field) = dlsym(api.h, sym)
+        LD(GetUniqueId, "ncclGetUniqueId");
+        LD(CommInitRank, "ncclCommInitRank");
+        LD(CommDestroy, "ncclCommDestroy");
+        LD(GroupStart, "ncclGroupStart");
+        LD(GroupEnd, "ncclGroupEnd");
+        LD(Send, "ncclSend");
+        LD(Recv, "ncclRecv");
+        LD(AlltoAll, "ncclAlltoAll");
+        LD(GetErrorString, "ncclGetErrorString");
+        LD(GetVersion, "ncclGetVersion");
+#undef LD
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
+    });
+    return api;
+}
+#define NC(x)                                                                                          \
+    do {                                                                                               \
+        int r_ = (x);                                                                                  \
+        if (r_ != 0) return fail(DFFT_ECOMM, "%s:%d NCCL call '%s' failed: %s", __FILE__, __LINE__, #x, \
+                                 nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "?");     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// cross-device flags for the fused (P2P) exchange
+// ------------------------------------------------------------------------------------------------
+struct SyncBlock {
+    unsigned long long arrive[DFFT_MAX_CHUNKS];  // arrive[s] = e : sender s finished writing my recv buffer for epoch e
+    unsigned long long ready[DFFT_MAX_CHUNKS];   // ready[r] = e  : receiver r finished reading its recv buffer of epoch e
+};
+struct FlagPtrs {
+    unsigned long long* p[DFFT_MAX_CHUNKS];
+};
+
+__global__ void signal_flags_kernel(FlagPtrs dst, int n, unsigned long long value)
+{
+    const int q = threadIdx.x;
+    if (q < n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst.p[q]), "l"(value) : "memory");
+    }
+}
+__global__ void wait_flags_kernel(const unsigned long long* flags, int n, unsigned long long value)
+{
+    const int q = threadIdx.x;
+    if (q < n) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + q) : "memory");
+            if (v < value) __nanosleep(200);
+        } while (v < value);
+    }
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct dfft_plan_s {
+    Geom g;
+    int P = 1, me = 0, direction = DFFT_FORWARD, prec = 0, device = 0, sms = 148;
+    unsigned flags = 0;
+    int xmode = DFFT_EXCHANGE_P2P;
+    size_t esz = 16;
+    long long n0l = 0, n1l = 0, in_count = 0, out_count = 0, max_count = 0;
+    void *in = nullptr, *out = nullptr, *buf1 = nullptr, *buf2 = nullptr, *recv = nullptr;
+    bool inplace = false;
+    const SizeEntry *ez = nullptr, *ey = nullptr, *ex = nullptr;   // axes N2 (Z), N1 (Y), N0 (X)
+    void *lut_z = nullptr, *lut_y = nullptr, *lut_x = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    dfft_comm comm = nullptr;
+    // p2p
+    std::vector<void*> peer_recv, peer_buf1;
+    SyncBlock* sync = nullptr;
+    std::vector<SyncBlock*> peer_sync;
+    std::vector<void*> ipc_opened;
+    unsigned long long epoch = 0;
+    // nccl
+    void* nccl = nullptr;
+    int launches = 0;
+    bool timed = false;
+};
+
+template <typename T> static void upload_lut(void** dst, int nstages, const int* rad)
+{
+    std::vector<cx<T>> lut = build_lut<T>(nstages, rad);
+    cudaMalloc(dst, lut.size() * sizeof(cx<T>));
+    cudaMemcpy(*dst, lut.data(), lut.size() * sizeof(cx<T>), cudaMemcpyHostToDevice);
+}
+
+static int share_pointer(dfft_plan p, void* mine, std::vector<void*>& peers)
+{
+    // make `mine` (a cudaMalloc allocation of this device) addressable by every rank
+    const int P = p->P;
+    peers.assign(P, nullptr);
+    if (p->comm->local) {
+        std::vector<void*> all(P);
+        p->comm->allgather(p->me, &mine, all.data(), sizeof(void*));
+        peers = all;
+        return 0;
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, mine));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    if (p->comm->allgather(p->me, &h, all.data(), sizeof(h)) != 0) return fail(DFFT_ECOMM, "bootstrap allgather failed");
+    for (int q = 0; q < P; q++) {
+        if (q == p->me) { peers[q] = mine; continue; }
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess));
+        peers[q] = ptr;
+        p->ipc_opened.push_back(ptr);
+    }
+    return 0;
+}
+
+extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* in, void* out, dfft_comm comm, int dev_idx,
+                                int P, int direction, int precision, unsigned flags, dfft_plan* plan_out)
+{
+    if (!plan_out) return fail(DFFT_EINVAL, "null plan pointer");
+    *plan_out = nullptr;
+    if (n0 < 1 || n1 < 1 || n2 < 1 || P < 1 || dev_idx < 0 || dev_idx >= P || !in)
+        return fail(DFFT_EINVAL, "dfft_plan_c2c_3d: bad arguments");
+    if (direction != DFFT_FORWARD && direction != DFFT_BACKWARD) return fail(DFFT_EINVAL, "direction must be +1 or -1");
+    if (precision != DFFT_DOUBLE && precision != DFFT_FLOAT) return fail(DFFT_EINVAL, "bad precision");
+    if (P > DFFT_MAX_CHUNKS) return fail(DFFT_EUNSUPPORTED, "at most %d devices", DFFT_MAX_CHUNKS);
+    if (P > 1 && (!comm || comm->nranks != P)) return fail(DFFT_EINVAL, "a communicator of %d ranks is required", P);
+    Geom g{n0, n1, n2, P};
+    if (g.last_n0() < 1 || g.last_n1() < 1)
+        return fail(DFFT_EUNSUPPORTED, "%lldx%lldx%lld cannot be split over %d devices (empty last slab); use dfft_init", n0, n1, n2, P);
+    const SizeEntry* ez = find_size_entry((int)n2, precision);
+    const SizeEntry* ey = find_size_entry((int)n1, precision);
+    const SizeEntry* ex = find_size_entry((int)n0, precision);
+    if (n0 > 1 << 20 || n1 > 1 << 20 || n2 > 1 << 20 || !ez || !ey || !ex)
+        return fail(DFFT_EUNSUPPORTED, "unsupported transform length in %lldx%lldx%lld (see dfft_supported_lengths)", n0, n1, n2);
+
+    dfft_plan p = new dfft_plan_s;
+    p->g = g; p->P = P; p->me = dev_idx; p->direction = direction; p->prec = precision; p->flags = flags;
+    p->esz = precision == DFFT_FLOAT ? 8 : 16;
+    p->n0l = g.n0l(dev_idx); p->n1l = g.n1l(dev_idx);
+    p->in_count = direction == DFFT_FORWARD ? g.in_count(dev_idx) : g.out_count(dev_idx);
+    p->out_count = direction == DFFT_FORWARD ? g.out_count(dev_idx) : g.in_count(dev_idx);
+    p->max_count = g.max_count(dev_idx);
+    p->ez = ez; p->ey = ey; p->ex = ex; p->comm = comm;
+    p->in = in; p->out = out;
+    int rc = 0;
+    auto bail = [&](int code) { dfft_destroy(p); return code; };
+#define CUP(x)                                                                                        \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return bail(fail(DFFT_ECUDA, "%s:%d CUDA call '%s' failed: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_))); \
+    } while (0)
+    CUP(cudaGetDevice(&p->device));
+    CUP(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    // buffers (api.cpp:66-77)
+    if (!out || out == in) { p->inplace = true; p->buf2 = in; }
+    else p->buf2 = out;
+    CUP(cudaMalloc(&p->buf1, (size_t)p->max_count * p->esz));
+    CUP(cudaMemcpy(p->buf1, in, (size_t)p->max_count * p->esz, cudaMemcpyDeviceToDevice));
+    CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto& e : p->ev) CUP(cudaEventCreate(&e));
+    if (precision == DFFT_DOUBLE) {
+        upload_lut<double>(&p->lut_z, ez->z_nstages, ez->z_rad);
+        upload_lut<double>(&p->lut_y, ey->s_nstages, ey->s_rad);
+        upload_lut<double>(&p->lut_x, ex->s_nstages, ex->s_rad);
+    } else {
+        upload_lut<float>(&p->lut_z, ez->z_nstages, ez->z_rad);
+        upload_lut<float>(&p->lut_y, ey->s_nstages, ey->s_rad);
+        upload_lut<float>(&p->lut_x, ex->s_nstages, ex->s_rad);
+    }
+    CUP(cudaGetLastError());
+
+    // exchange mode
+    int xmode = (int)(flags & DFFT_EXCHANGE_MASK);
+    if (P == 1) xmode = xmode == DFFT_EXCHANGE_STAGED ? DFFT_EXCHANGE_STAGED : DFFT_EXCHANGE_P2P;
+    else if (xmode == DFFT_EXCHANGE_AUTO) {
+        const char* env = getenv("DFFT_EXCHANGE");
+        if (env && !strcmp(env, "nccl")) xmode = DFFT_EXCHANGE_NCCL;
+        else if (env && !strcmp(env, "staged")) xmode = DFFT_EXCHANGE_STAGED;
+        else xmode = DFFT_EXCHANGE_P2P;
+    }
+    p->xmode = xmode;
+    if (P > 1) {
+        if (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_STAGED) {
+            if (xmode == DFFT_EXCHANGE_P2P) {
+                CUP(cudaMalloc(&p->recv, (size_t)p->max_count * p->esz));
+                if ((rc = share_pointer(p, p->recv, p->peer_recv)) != 0) return bail(rc);
+            } else {
+                if ((rc = share_pointer(p, p->buf1, p->peer_buf1)) != 0) return bail(rc);
+            }
+            CUP(cudaMalloc((void**)&p->sync, sizeof(SyncBlock)));
+            CUP(cudaMemset(p->sync, 0, sizeof(SyncBlock)));
+            std::vector<void*> ps;
+            if ((rc = share_pointer(p, p->sync, ps)) != 0) return bail(rc);
+            p->peer_sync.resize(P);
+            for (int q = 0; q < P; q++) p->peer_sync[q] = (SyncBlock*)ps[q];
+        } else {
+            NcclApi& api = nccl_api();
+            if (!api.ok) return bail(fail(DFFT_ECOMM, "libnccl.so.2 could not be loaded (set DFFT_NCCL_LIB)"));
+            NcclUid uid;
+            memset(&uid, 0, sizeof(uid));
+            if (p->me == 0) {
+                int r = api.GetUniqueId(&uid);
+                if (r != 0) return bail(fail(DFFT_ECOMM, "ncclGetUniqueId failed"));
+            }
+            std::vector<NcclUid> all(P);
+            if (comm->allgather(p->me, &uid, all.data(), sizeof(uid)) != 0) return bail(fail(DFFT_ECOMM, "bootstrap allgather failed"));
+            int r = api.CommInitRank(&p->nccl, P, all[0], p->me);
+            if (r != 0) return bail(fail(DFFT_ECOMM, "ncclCommInitRank failed: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
+        }
+        comm->host_barrier(p->me);
+    }
+    CUP(cudaDeviceSynchronize());
+#undef CUP
+    *plan_out = p;
+    return 0;
+}
+
+extern "C" int dfft_destroy(dfft_plan p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->P > 1 && p->comm && (p->sync || p->nccl)) p->comm->host_barrier(p->me);   // nobody still writes into my buffers
+    if (p->nccl) nccl_api().CommDestroy(p->nccl);
+    for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+    if (p->P > 1 && p->comm && !p->comm->local && !p->ipc_opened.empty()) p->comm->host_barrier(p->me);
+    if (p->buf1) cudaFree(p->buf1);
+    if (p->recv) cudaFree(p->recv);
+    if (p->sync) cudaFree(p->sync);
+    if (p->lut_z) cudaFree(p->lut_z);
+    if (p->lut_y) cudaFree(p->lut_y);
+    if (p->lut_x) cudaFree(p->lut_x);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    cudaGetLastError();
+    delete p;
+    return 0;
+}
+
+extern "C" int dfft_cleanup(void) { return 0; }
+
+extern "C" int dfft_memcpy(void* dst, const void* src, size_t bytes, int kind)
+{
+    CU(cudaMemcpy(dst, src, bytes, kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDefault)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass launches
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Pass {
+    static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a)
+    {
+        a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
+        cudaError_t err = e->launch[kind](&a, p->sms, p->stream);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "pass launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
+    }
+    // contiguous lines of length N2 in `buf` (n0l*N1 lines), in place
+    static int z_pass(dfft_plan p, void* buf, bool scale)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ez->z_C;
+        const long long nlines = p->n0l * g.n1;
+        a.in = (const cx<T>*)buf; a.out = (cx<T>*)buf; a.lut = (const cx<T>*)p->lut_z;
+        a.G = (int)cdiv(nlines, C); a.W = (int)std::min<long long>(nlines, 0x7fffffff); a.ntiles = a.G;
+        a.ia = Affine{0, (long long)C * g.n2, g.n2, 1}; a.oa = a.ia;
+        a.do_scale = scale ? 1 : 0; a.scale = (T)(1.0 / ((double)g.n0 * (double)g.n1 * (double)g.n2));
+        return launch(p, p->ez, PK_Z, a);
+    }
+    // columns of length N1 (stride N2) of every local plane.  mode 0: src -> dst natural (in place when equal)
+    // mode 1: chunked (packed / peer) store, mode 2: chunked (unpack) load
+    static int y_pass(dfft_plan p, const void* src, void* dst, int mode, void* const* chunk_base)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ey->s_C;
+        a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_y;
+        a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n0l * a.G;
+        a.ia = Affine{g.n1 * g.n2, C, 1, g.n2}; a.oa = a.ia;
+        if (mode != 0) {
+            ChunkTab& ct = mode == 1 ? a.co : a.ci;
+            ct.ediv = (int)g.yd(); ct.nchunks = p->P;
+            for (int q = 0; q < p->P; q++) { ct.cptr[q] = chunk_base[q]; ct.SAq[q] = g.n1l(q) * g.n2; }
+        }
+        return launch(p, p->ey, mode == 0 ? PK_Y : (mode == 1 ? PK_Y_CO : PK_Y_CI), a);
+    }
+    // forward X: src = [x][y_l][z] -> dst = [y_l][z][x]
+    static int x_fwd(dfft_plan p, const void* src, void* dst)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ex->s_C;
+        a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_x;
+        a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n1l * a.G;
+        a.ia = Affine{g.n2, C, 1, p->n1l * g.n2};
+        a.oa = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
+        return launch(p, p->ex, PK_XF, a);
+    }
+    // backward X: src = [y_l][z][x] -> dst = [x][y_l][z] (chunked by destination device when chunk_base)
+    static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ex->s_C;
+        a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_x;
+        a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n1l * a.G;
+        a.ia = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
+        a.oa = Affine{g.n2, C, 1, p->n1l * g.n2};
+        if (chunk_base) {
+            a.co.ediv = (int)g.xd(); a.co.nchunks = p->P;
+            for (int q = 0; q < p->P; q++) { a.co.cptr[q] = chunk_base[q]; a.co.SAq[q] = g.n2; }
+        }
+        return launch(p, p->ex, chunk_base ? PK_XB_CO : PK_XB, a);
+    }
+};
+
+static inline char* eoff(void* base, long long elems, size_t esz) { return (char*)base + (size_t)elems * esz; }
+
+// exchange offsets (api.cpp:84-133, 613-627): where chunk (sender s -> receiver r) starts
+static long long send_off(const Geom& g, int s, int r, int dir)
+{
+    return dir == DFFT_FORWARD ? (long long)r * g.n0l(s) * g.yd() * g.n2 : (long long)r * g.xd() * g.n1l(s) * g.n2;
+}
+static long long recv_off(const Geom& g, int s, int r, int dir)
+{
+    return dir == DFFT_FORWARD ? (long long)s * g.xd() * g.n1l(r) * g.n2 : (long long)s * g.n0l(r) * g.yd() * g.n2;
+}
+static long long xchg_count(const Geom& g, int s, int r, int dir)
+{
+    return dir == DFFT_FORWARD ? g.n0l(s) * g.n1l(r) * g.n2 : g.n0l(r) * g.n1l(s) * g.n2;
+}
+
+static int flags_signal(dfft_plan p, bool arrive, unsigned long long value)
+{
+    FlagPtrs fp{};
+    for (int q = 0; q < p->P; q++) fp.p[q] = arrive ? &p->peer_sync[q]->arrive[p->me] : &p->peer_sync[q]->ready[p->me];
+    signal_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, p->stream>>>(fp, p->P, value);
+    CU(cudaGetLastError());
+    p->launches++;
+    return 0;
+}
+static int flags_wait(dfft_plan p, bool arrive, unsigned long long value)
+{
+    if (value == 0) return 0;
+    wait_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, p->stream>>>(arrive ? p->sync->arrive : p->sync->ready, p->P, value);
+    CU(cudaGetLastError());
+    p->launches++;
+    return 0;
+}
+
+static int nccl_exchange(dfft_plan p, const void* sendbuf, void* recvbuf)
+{
+    NcclApi& api = nccl_api();
+    const Geom& g = p->g;
+    const int dir = p->direction;
+    bool even = true;
+    for (int q = 0; q < p->P; q++)
+        if (xchg_count(g, p->me, q, dir) != xchg_count(g, 0, 0, dir) || xchg_count(g, q, p->me, dir) != xchg_count(g, 0, 0, dir)) even = false;
+    if (even && api.AlltoAll && !getenv("DFFT_NCCL_SENDRECV")) {
+        NC(api.AlltoAll(sendbuf, recvbuf, (size_t)xchg_count(g, 0, 0, dir) * p->esz, /*ncclInt8*/ 0, p->nccl, p->stream));
+    } else {
+        NC(api.GroupStart());
+        for (int q = 0; q < p->P; q++) {
+            NC(api.Send(eoff((void*)sendbuf, send_off(g, p->me, q, dir), p->esz), (size_t)xchg_count(g, p->me, q, dir) * p->esz, 0, q, p->nccl, p->stream));
+            NC(api.Recv(eoff(recvbuf, recv_off(g, q, p->me, dir), p->esz), (size_t)xchg_count(g, q, p->me, dir) * p->esz, 0, q, p->nccl, p->stream));
+        }
+        NC(api.GroupEnd());
+    }
+    p->launches++;
+    return 0;
+}
+
+template <typename T> static int execute_fused(dfft_plan p)
+{
+    const Geom& g = p->g;
+    const int P = p->P, me = p->me;
+    int rc;
+    p->launches = 0;
+    CU(cudaEventRecord(p->ev[0], p->stream));
+    if (p->direction == DFFT_FORWARD) {
+        // t0 (+t1): Z pass in place, Y pass with the pack (and, P2P, the all-to-all) folded into its store
+        if ((rc = Pass<T>::z_pass(p, p->buf1, false))) return rc;
+        if (P == 1) {
+            if ((rc = Pass<T>::y_pass(p, p->buf1, p->buf1, 0, nullptr))) return rc;
+            CU(cudaEventRecord(p->ev[1], p->stream));
+            CU(cudaEventRecord(p->ev[2], p->stream));
+            if ((rc = Pass<T>::x_fwd(p, p->buf1, p->buf2))) return rc;
+        } else if (p->xmode == DFFT_EXCHANGE_P2P) {
+            p->epoch++;
+            if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
+            void* base[DFFT_MAX_CHUNKS];
+            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_recv[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
+            if ((rc = Pass<T>::y_pass(p, p->buf1, nullptr, 1, base))) return rc;
+            if ((rc = flags_signal(p, true, p->epoch))) return rc;
+            CU(cudaEventRecord(p->ev[1], p->stream));
+            if ((rc = flags_wait(p, true, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
+            CU(cudaEventRecord(p->ev[2], p->stream));
+            if ((rc = Pass<T>::x_fwd(p, p->recv, p->buf2))) return rc;
+            if ((rc = flags_signal(p, false, p->epoch))) return rc;
+        } else {
+            void* base[DFFT_MAX_CHUNKS];
+            for (int q = 0; q < P; q++) base[q] = eoff(p->buf2, send_off(g, me, q, DFFT_FORWARD), p->esz);
+            if ((rc = Pass<T>::y_pass(p, p->buf1, nullptr, 1, base))) return rc;
+            CU(cudaEventRecord(p->ev[1], p->stream));
+            if ((rc = nccl_exchange(p, p->buf2, p->buf1))) return rc;
+            CU(cudaEventRecord(p->ev[2], p->stream));
+            if ((rc = Pass<T>::x_fwd(p, p->buf1, p->buf2))) return rc;
+        }
+        CU(cudaEventRecord(p->ev[3], p->stream));
+    } else {
+        const bool scale = (p->flags & DFFT_SCALE_BACKWARD) != 0;
+        if (P == 1) {
+            if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
+            CU(cudaEventRecord(p->ev[1], p->stream));
+            CU(cudaEventRecord(p->ev[2], p->stream));
+            if ((rc = Pass<T>::y_pass(p, p->buf2, p->buf2, 0, nullptr))) return rc;
+        } else if (p->xmode == DFFT_EXCHANGE_P2P) {
+            p->epoch++;
+            if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;
+            void* base[DFFT_MAX_CHUNKS];
+            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_recv[q], recv_off(g, me, q, DFFT_BACKWARD), p->esz);
+            if ((rc = Pass<T>::x_bwd(p, p->buf1, nullptr, base))) return rc;
+            if ((rc = flags_signal(p, true, p->epoch))) return rc;
+            CU(cudaEventRecord(p->ev[1], p->stream));
+            if ((rc = flags_wait(p, true, p->epoch))) return rc;
+            CU(cudaEventRecord(p->ev[2], p->stream));
+            void* cb[DFFT_MAX_CHUNKS];
+            for (int q = 0; q < P; q++) cb[q] = eoff(p->recv, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
+            if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
+            if ((rc = flags_signal(p, false, p->epoch))) return rc;
+        } else {
+            if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
+            CU(cudaEventRecord(p->ev[1], p->stream));
+            if ((rc = nccl_exchange(p, p->buf2, p->buf1))) return rc;
+            CU(cudaEventRecord(p->ev[2], p->stream));
+            void* cb[DFFT_MAX_CHUNKS];
+            for (int q = 0; q < P; q++) cb[q] = eoff(p->buf1, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
+            if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
+        }
+        if ((rc = Pass<T>::z_pass(p, p->buf2, scale))) return rc;
+        CU(cudaEventRecord(p->ev[3], p->stream));
+    }
+    p->timed = true;
+    return 0;
+}
+
+// reference-like stage-by-stage execution (api.cpp:181-214 with its device-wide syncs)
+template <typename T> static int execute_stage(dfft_plan p, int stage)
+{
+    const Geom& g = p->g;
+    const int P = p->P, me = p->me, dir = p->direction;
+    int rc = 0;
+    // map "k-th executed stage" to the reference stage id
+    const int sid = dir == DFFT_FORWARD ? stage : 3 - stage;
+    if (sid == 0) {          // fftZY
+        void* buf = dir == DFFT_FORWARD ? p->buf1 : p->buf2;
+        if (dir == DFFT_FORWARD) {
+            if ((rc = Pass<T>::z_pass(p, buf, false))) return rc;
+            if ((rc = Pass<T>::y_pass(p, buf, buf, 0, nullptr))) return rc;
+        } else {
+            if ((rc = Pass<T>::y_pass(p, buf, buf, 0, nullptr))) return rc;
+            if ((rc = Pass<T>::z_pass(p, buf, (p->flags & DFFT_SCALE_BACKWARD) != 0))) return rc;
+        }
+    } else if (sid == 1) {   // localTransposeUneven
+        cudaError_t e = launch_pack_rows(p->buf1, p->buf2, (int)p->esz, p->n0l, g.n1, g.n2, P, dir == DFFT_FORWARD, p->sms, p->stream);
+        if (e != cudaSuccess) return fail(DFFT_ECUDA, "pack launch failed: %s", cudaGetErrorString(e));
+        p->launches++;
+    } else if (sid == 2) {   // slabAlltoall
+        if (P > 1) {
+            CU(cudaStreamSynchronize(p->stream));
+            p->comm->host_barrier(me);   // every sender's buf2 is packed, every receiver's buf1 is free
+            for (int q = 0; q < P; q++) {
+                CU(cudaMemcpyAsync(eoff(p->peer_buf1[q], recv_off(g, me, q, dir), p->esz), eoff(p->buf2, send_off(g, me, q, dir), p->esz),
+                                   (size_t)xchg_count(g, me, q, dir) * p->esz, cudaMemcpyDefault, p->stream));
+                p->launches++;
+            }
+            CU(cudaStreamSynchronize(p->stream));
+            p->comm->host_barrier(me);
+        } else {
+            CU(cudaMemcpyAsync(p->buf1, p->buf2, (size_t)p->in_count * p->esz, cudaMemcpyDeviceToDevice, p->stream));
+            p->launches++;
+        }
+    } else {                 // fftX
+        if (dir == DFFT_FORWARD) rc = Pass<T>::x_fwd(p, p->buf1, p->buf2);
+        else rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int dfft_execute_stage(dfft_plan p, int stage)
+{
+    if (!p || stage < 0 || stage > 3) return fail(DFFT_EINVAL, "dfft_execute_stage: bad arguments");
+    if (p->xmode != DFFT_EXCHANGE_STAGED) return fail(DFFT_EINVAL, "dfft_execute_stage needs a plan created with DFFT_EXCHANGE_STAGED");
+    CU(cudaSetDevice(p->device));
+    return p->prec == DFFT_DOUBLE ? execute_stage<double>(p, stage) : execute_stage<float>(p, stage);
+}
+
+extern "C" int dfft_execute(dfft_plan p)
+{
+    if (!p) return fail(DFFT_EINVAL, "null plan");
+    CU(cudaSetDevice(p->device));
+    if (p->xmode == DFFT_EXCHANGE_STAGED) {
+        p->launches = 0;
+        for (int s = 0; s < 4; s++) {
+            CU(cudaEventRecord(p->ev[s], p->stream));
+            int rc = p->prec == DFFT_DOUBLE ? execute_stage<double>(p, s) : execute_stage<float>(p, s);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(p->ev[4], p->stream));
+        p->timed = true;
+        return 0;
+    }
+    return p->prec == DFFT_DOUBLE ? execute_fused<double>(p) : execute_fused<float>(p);
+}
+
+extern "C" int dfft_synchronize(dfft_plan p)
+{
+    if (!p) return fail(DFFT_EINVAL, "null plan");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int dfft_get_timings(dfft_plan p, double t[5])
+{
+    if (!p || !t) return fail(DFFT_EINVAL, "bad arguments");
+    if (!p->timed) return fail(DFFT_EINVAL, "no execute to time yet");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    float ms[4] = {0, 0, 0, 0};
+    if (p->xmode == DFFT_EXCHANGE_STAGED) {
+        for (int s = 0; s < 4; s++) CU(cudaEventElapsedTime(&ms[s], p->ev[s], p->ev[s + 1]));
+        if (p->direction == DFFT_BACKWARD) { std::swap(ms[0], ms[3]); std::swap(ms[1], ms[2]); }
+        for (int s = 0; s < 4; s++) t[s] = ms[s];
+    } else {
+        float a, b, c;
+        CU(cudaEventElapsedTime(&a, p->ev[0], p->ev[1]));
+        CU(cudaEventElapsedTime(&b, p->ev[1], p->ev[2]));
+        CU(cudaEventElapsedTime(&c, p->ev[2], p->ev[3]));
+        if (p->direction == DFFT_FORWARD) { t[0] = a; t[1] = 0; t[2] = b; t[3] = c; }
+        else { t[3] = a; t[2] = b; t[1] = 0; t[0] = c; }
+    }
+    t[4] = t[0] + t[1] + t[2] + t[3];
+    return 0;
+}
+
+extern "C" int dfft_execute_host(dfft_plan p, const void* host_in, void* host_out)
+{
+    if (!p || !host_in || !host_out) return fail(DFFT_EINVAL, "bad arguments");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(p->buf1, host_in, (size_t)p->in_count * p->esz, cudaMemcpyHostToDevice, p->stream));
+    int rc = dfft_execute(p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host_out, p->buf2, (size_t)p->out_count * p->esz, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int dfft_plan_buffers(dfft_plan p, void** b1, void** b2)
+{
+    if (!p) return fail(DFFT_EINVAL, "null plan");
+    if (b1) *b1 = p->buf1;
+    if (b2) *b2 = p->buf2;
+    return 0;
+}
+extern "C" int dfft_plan_counts(dfft_plan p, long long* ic, long long* oc, long long* mc)
+{
+    if (!p) return fail(DFFT_EINVAL, "null plan");
+    if (ic) *ic = p->in_count;
+    if (oc) *oc = p->out_count;
+    if (mc) *mc = p->max_count;
+    return 0;
+}
+extern "C" int dfft_plan_launches(dfft_plan p) { return p ? p->launches : 0; }
+extern "C" int dfft_plan_exchange(dfft_plan p) { return p ? p->xmode : 0; }
+extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------
+// batched local transforms
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int fft_lines_impl(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
+                          long long outer_dist, int direction, const SizeEntry* e)
+{
+    int sms = 0, dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TileArgs<T> a{};
+    a.in = (const cx<T>*)data; a.out = (cx<T>*)data;
+    a.inv = direction == DFFT_BACKWARD;
+    void* lut = nullptr;
+    int kind;
+    if (stride == 1) {
+        if (inner_dist != n || (inner != nlines && outer_dist != inner * n)) return fail(DFFT_EUNSUPPORTED, "contiguous lines must be densely packed");
+        upload_lut<T>(&lut, e->z_nstages, e->z_rad);
+        const int C = e->z_C;
+        a.G = (int)cdiv(nlines, C); a.W = (int)nlines; a.ntiles = a.G;
+        a.ia = Affine{0, (long long)C * n, n, 1};
+        kind = PK_Z;
+    } else {
+        if (inner_dist != 1 || inner < 1 || nlines % inner) return fail(DFFT_EUNSUPPORTED, "strided lines must be columns (inner_dist == 1)");
+        upload_lut<T>(&lut, e->s_nstages, e->s_rad);
+        const int C = e->s_C;
+        a.G = (int)cdiv(inner, C); a.W = (int)inner; a.ntiles = (nlines / inner) * a.G;
+        a.ia = Affine{outer_dist, C, 1, stride};
+        kind = PK_Y;
+    }
+    a.oa = a.ia; a.lut = (const cx<T>*)lut;
+    cudaError_t err = e->launch[kind](&a, sms, 0);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    cudaFree(lut);
+    if (err != cudaSuccess) return fail(DFFT_ECUDA, "fft_lines failed: %s", cudaGetErrorString(err));
+    return 0;
+}
+
+extern "C" int dfft_fft_lines(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
+                              long long outer_dist, int direction, int precision)
+{
+    if (!data || n < 1 || nlines < 0 || stride < 1) return fail(DFFT_EINVAL, "bad arguments");
+    const SizeEntry* e = find_size_entry(n, precision);
+    if (!e) return fail(DFFT_EUNSUPPORTED, "unsupported length %d", n);
+    if (nlines == 0) return 0;
+    return precision == DFFT_DOUBLE ? fft_lines_impl<double>(data, n, stride, nlines, inner, inner_dist, outer_dist, direction, e)
+                                    : fft_lines_impl<float>(data, n, stride, nlines, inner, inner_dist, outer_dist, direction, e);
+}

@@ -1,0 +1,45 @@
+// dfft_kernels.cuh -- table of pre-instantiated pass kernels, one entry per (length, precision).
+// The reference compiles one kernel per axis at plan time with hiprtc
+// (templateFFT/src/templateFFT.cpp:5614-5752); here the supported lengths are instantiated ahead
+// of time for sm_100a and looked up at plan time.
+#pragma once
+#include <cuda_runtime.h>
+#include <vector>
+#include "fft_passes.cuh"
+
+namespace dfft {
+
+enum PassKind {
+    PK_Z = 0,      // contiguous lines, MAP_T -> MAP_T
+    PK_Y,          // strided, MAP_C -> MAP_C
+    PK_Y_CO,       // + chunked (pack / peer) store
+    PK_Y_CI,       // + chunked (unpack) load
+    PK_XF,         // strided load, transposed contiguous store (MAP_C -> MAP_T)
+    PK_XB,         // contiguous load, strided store (MAP_T -> MAP_C)
+    PK_XB_CO,      // + chunked (peer) store
+    PK_COUNT
+};
+
+typedef cudaError_t (*PassLaunchFn)(const void* tile_args, int sm_count, cudaStream_t stream);
+
+struct SizeEntry {
+    int N;
+    int prec;             // 0 = double, 1 = float
+    int z_C, s_C;         // lines per tile of the contiguous / strided kernels
+    int z_nstages, z_rad[8];
+    int s_nstages, s_rad[8];
+    PassLaunchFn launch[PK_COUNT];
+};
+
+const SizeEntry* find_size_entry(int N, int prec);
+void list_sizes(int prec, std::vector<int>& out);
+
+// twiddle table of a radix list, layout of Sched::lut_off(): per stage s >= 1,
+// entry (m-1)*NS + k = e^{-2 pi i k m / (NS * RAD)}; evaluated in long double, rounded once.
+template <typename T> std::vector<cx<T>> build_lut(int nstages, const int* rad);
+
+// element-wise helpers (staged reference-like mode, tests)
+cudaError_t launch_pack_rows(const void* in, void* out, int elem_bytes, long long x_size, long long n1, long long n2,
+                             int P, int forward, int sm_count, cudaStream_t st);
+
+}  // namespace dfft

@@ -337,17 +337,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase)
 {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return ok != 0;
+}
+// bounded wait: a transaction that never completes (bad size/alignment) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    for (uint32_t spins = 0; !mbar_try_wait(bar, phase); spins++)
+        if (spins > (1u << 26)) __trap();
 }
 __device__ __forceinline__ void fence_barrier_init()
 {
@@ -366,6 +371,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 
 // Stage the per-length twiddle table (global, built at plan time) into shared memory with one
 // TMA bulk copy issued by thread 0; everyone waits on the mbarrier.  `bar` and `dst` in smem.
+// The global table is allocated padded to a multiple of 16 bytes (build_lut), `dst` is 16-byte aligned.
 template <typename T>
 __device__ __forceinline__ void stage_twiddles_tma(cx<T>* dst, const cx<T>* __restrict__ src, int entries, uint64_t* bar)
 {
@@ -376,7 +382,7 @@ __device__ __forceinline__ void stage_twiddles_tma(cx<T>* dst, const cx<T>* __re
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)(entries * sizeof(cx<T>));
+        const uint32_t bytes = (uint32_t)((entries * sizeof(cx<T>) + 15) / 16 * 16);
         mbar_expect_tx(bar, bytes);
         tma_bulk_g2s(dst, src, bytes, bar);
     }

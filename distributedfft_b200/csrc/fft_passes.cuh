@@ -38,14 +38,16 @@ template <typename T> struct TileArgs {
     long long ntiles;      // total tiles
     int G;                 // tiles per `a`
     int W;                 // columns per `a` (for the ragged last tile: valid = min(C, W - b*C))
-    T scale;               // applied on store when SCALE
+    T scale;               // applied on store when do_scale
+    int inv;               // 1: inverse transform (e^{+i..}), unnormalised
+    int do_scale;
     ChunkTab ci, co;       // used when CHUNK_IN / CHUNK_OUT
 };
 
 template <class S, typename T, int C, bool PINGPONG>
 struct TileSmem {
     static constexpr int LS = SmemGeom<T>::line(S::N, C);
-    static constexpr size_t exch_bytes = (S::NSTAGES > 1 ? (PINGPONG ? 2 : 1) : 0) * (size_t)C * LS * sizeof(cx<T>);
+    static constexpr size_t exch_bytes = ((S::NSTAGES > 1 ? (PINGPONG ? 2 : 1) : 0) * (size_t)C * LS * sizeof(cx<T>) + 15) / 16 * 16;
     static constexpr size_t lut_bytes = (size_t)((S::lut_size() * sizeof(cx<T>) + 15) / 16 * 16);
     static constexpr size_t tab_bytes = (size_t)S::N * sizeof(int2) * 2 + 2 * DFFT_MAX_CHUNKS * 16;
     static constexpr size_t bytes(bool chunked) { return exch_bytes + lut_bytes + 16 + (chunked ? tab_bytes : 0); }
@@ -95,11 +97,12 @@ template <int MAP, int C, int TT> __device__ __forceinline__ void thread_map(int
 template <typename C_> __device__ __forceinline__ C_ ld_stream(const C_* p) { return __ldcg(p); }
 template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { __stcg(p, v); }
 
-template <class S, typename T, int C, int MAPIN, int MAPOUT, bool INV, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT,
-          bool PREFETCH, bool SCALE, int MINB, bool PINGPONG = true>
+template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, int MINB,
+          bool PINGPONG>
 __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<T> A)
 {
     static_assert(S::valid(), "bad schedule");
+    static_assert(S::NSTAGES > 1 || MAPIN == MAPOUT, "a thread-map change needs an exchange");
     using SM = TileSmem<S, T, C, PINGPONG>;
     constexpr int R = S::R, TT = S::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,75 +139,61 @@ __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<
     cx<T> twr[TWREG ? (S::tw_regs_total() > 0 ? S::tw_regs_total() : 1) : 1];
     if constexpr (TWREG) TwLoader<S, 0, T>::run(twr, t_in, t_out, lut_s);
 
-    auto load_tile = [&](cx<T>* v, long long tile) {
-        const long long a = tile / A.G;
-        const int b = (int)(tile - a * A.G);
-        const bool ok = b * C + c_in < A.W;
-        if constexpr (!CHUNK_IN) {
-            const cx<T>* p = A.in + a * A.ia.SA + b * A.ia.SB + c_in * A.ia.cs + (long long)t_in * A.ia.es;
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                cx<T> x = ok ? ld_stream(p + (long long)u * TT * A.ia.es) : mk<T>(0, 0);
-                v[u] = INV ? cswap(x) : x;
-            }
-        } else {
-            const long long off = b * A.ia.SB + c_in * A.ia.cs;
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                const int2 qe = etab_i[t_in + u * TT];
-                const cx<T>* p = reinterpret_cast<const cx<T>*>(cptr_i[qe.x]) + a * saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
-                cx<T> x = ok ? ld_stream(p) : mk<T>(0, 0);
-                v[u] = INV ? cswap(x) : x;
-            }
-        }
-    };
-    auto store_tile = [&](const cx<T>* v, long long tile) {
-        const long long a = tile / A.G;
-        const int b = (int)(tile - a * A.G);
-        const bool ok = b * C + c_out < A.W;
-        if (!ok) return;
-        if constexpr (!CHUNK_OUT) {
-            cx<T>* p = A.out + a * A.oa.SA + b * A.oa.SB + c_out * A.oa.cs + (long long)t_out * A.oa.es;
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                cx<T> x = INV ? cswap(v[u]) : v[u];
-                if constexpr (SCALE) { x.x *= A.scale; x.y *= A.scale; }
-                st_stream(p + (long long)u * TT * A.oa.es, x);
-            }
-        } else {
-            const long long off = b * A.oa.SB + c_out * A.oa.cs;
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                const int2 qe = etab_o[t_out + u * TT];
-                cx<T>* p = reinterpret_cast<cx<T>*>(cptr_o[qe.x]) + a * saq_o[qe.x] + off + (long long)qe.y * A.oa.es;
-                cx<T> x = INV ? cswap(v[u]) : v[u];
-                if constexpr (SCALE) { x.x *= A.scale; x.y *= A.scale; }
-                st_stream(p, x);
-            }
-        }
-    };
+    const bool inv = A.inv != 0;   // inverse transform = swap(re,im) -> forward -> swap(re,im)
+    const bool do_scale = A.do_scale != 0;
 
     int pp = 0;
-    long long tile = blockIdx.x;
-    cx<T> cur[R];
-    if constexpr (PREFETCH) {
-        if (tile < A.ntiles) load_tile(cur, tile);
-    }
-    while (tile < A.ntiles) {
-        const long long next = tile + gridDim.x;
-        cx<T> nxt[PREFETCH ? R : 1];
-        if constexpr (PREFETCH) {
-            if (next < A.ntiles) load_tile(nxt, next);
-        } else {
-            load_tile(cur, tile);
-        }
-        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(cur, t_in, c_in, t_out, c_out, exch, pp, lut_s, twr);
-        store_tile(cur, tile);
-        if constexpr (PREFETCH) {
+    for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const long long a = tile / A.G;
+        const int b = (int)(tile - a * A.G);
+        cx<T> v[R];
+        {
+            const bool ok = b * C + c_in < A.W;
+            if constexpr (!CHUNK_IN) {
+                const cx<T>* p = A.in + a * A.ia.SA + b * A.ia.SB + c_in * A.ia.cs + (long long)t_in * A.ia.es;
 #pragma unroll
-            for (int u = 0; u < R; u++) cur[u] = nxt[u];
+                for (int u = 0; u < R; u++) v[u] = ok ? ld_stream(p + (long long)u * TT * A.ia.es) : mk<T>(0, 0);
+            } else {
+                const long long off = b * A.ia.SB + c_in * A.ia.cs;
+#pragma unroll
+                for (int u = 0; u < R; u++) {
+                    const int2 qe = etab_i[t_in + u * TT];
+                    const cx<T>* p = reinterpret_cast<const cx<T>*>(cptr_i[qe.x]) + a * saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
+                    v[u] = ok ? ld_stream(p) : mk<T>(0, 0);
+                }
+            }
+            if (inv) {
+#pragma unroll
+                for (int u = 0; u < R; u++) v[u] = cswap(v[u]);
+            }
         }
-        tile = next;
+        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, exch, pp, lut_s, twr);
+        {
+            if (inv) {
+#pragma unroll
+                for (int u = 0; u < R; u++) v[u] = cswap(v[u]);
+            }
+            if (do_scale) {
+#pragma unroll
+                for (int u = 0; u < R; u++) { v[u].x *= A.scale; v[u].y *= A.scale; }
+            }
+            const bool ok = b * C + c_out < A.W;
+            if (ok) {
+                if constexpr (!CHUNK_OUT) {
+                    cx<T>* p = A.out + a * A.oa.SA + b * A.oa.SB + c_out * A.oa.cs + (long long)t_out * A.oa.es;
+#pragma unroll
+                    for (int u = 0; u < R; u++) st_stream(p + (long long)u * TT * A.oa.es, v[u]);
+                } else {
+                    const long long off = b * A.oa.SB + c_out * A.oa.cs;
+#pragma unroll
+                    for (int u = 0; u < R; u++) {
+                        const int2 qe = etab_o[t_out + u * TT];
+                        cx<T>* p = reinterpret_cast<cx<T>*>(cptr_o[qe.x]) + a * saq_o[qe.x] + off + (long long)qe.y * A.oa.es;
+                        st_stream(p, v[u]);
+                    }
+                }
+            }
+        }
     }
 }
 

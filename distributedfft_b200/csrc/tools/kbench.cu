@@ -65,7 +65,7 @@ void run_variant(const char* name, int pass /*0 Z,1 Y,2 X*/, int ctas_per_sm)
     using T = double;
     if (g_only >= 0 && g_idx++ != g_only) return;
     if (g_only < 0) g_idx++;
-    auto kern = fft_tile_kernel<S, T, C, MAPIN, MAPOUT, false, TWREG, false, false, PREFETCH, false, MINB, PP>;
+    auto kern = fft_tile_kernel<S, T, C, MAPIN, MAPOUT, TWREG, false, false, MINB, PP>;
     using SM = TileSmem<S, T, C, PP>;
     size_t smem = SM::bytes(false);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,150 @@
+/*
+ * dfft.h -- C ABI of the B200-native slab-decomposed 3-D complex-to-complex FFT (libdfft.so).
+ *
+ * This is the drop-in boundary for the hot path of lueelu/DistributedFFT's `3dmpifft_opt`:
+ * every entry point below names the reference interface it replaces (paths relative to the
+ * reference tree).  Plain pointers and sizes only; all functions return 0 on success and a
+ * negative DFFT_E* code on failure (dfft_last_error() gives the message).  The reference aborts
+ * with exit(EXIT_FAILURE) on every error (3dmpifft_opt/include/fft_mpi_common.h:31-102); the C++
+ * shim include/fft_mpi_3d_api.h keeps that behaviour on top of this ABI.
+ *
+ * Data model (identical to the reference):
+ *   global array A[x][y][z], z fastest, N0 = X slowest; P devices; device p owns the x-slab
+ *   [p*xd, p*xd + n0_l), xd = ceil(N0/P), the last device the remainder.
+ *   forward : in = natural x-slab [x_l][y][z]  ->  out = y-slab, TRANSPOSED [y_l][z][x] (x fastest)
+ *   backward: in = [y_l][z][x]                 ->  out = natural [x_l][y][z], unnormalised.
+ *   complex = interleaved (re, im) doubles (precision 0) or floats (precision 1).
+ *
+ * Threading: a plan belongs to one device; one host thread per device may create/execute plans
+ * concurrently (the reference's `#pragma omp parallel for num_threads(devices)` loop,
+ * 3dmpifft_opt/fftSpeed3d_c2c.cpp:49), or one process per device (torchrun) with a bootstrap
+ * callback.  Collective calls (plan creation with P > 1, execute with P > 1, destroy) must be made
+ * by all P participants.
+ */
+#ifndef DFFT_H
+#define DFFT_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFFT_FORWARD 1      /* fft_mpi_common.h:18 FORWARD  */
+#define DFFT_BACKWARD (-1)  /* fft_mpi_common.h:19 BACKWARD */
+#define DFFT_ALLOC_CPU 1    /* fft_mpi_common.h:15 ALLOC_CPU (pinned host memory here) */
+#define DFFT_ALLOC_DEV (-1) /* fft_mpi_common.h:16 ALLOC_DEV */
+
+#define DFFT_DOUBLE 0
+#define DFFT_FLOAT 1
+
+/* plan flags */
+#define DFFT_EXCHANGE_AUTO 0u    /* P2P when every peer is reachable, else NCCL */
+#define DFFT_EXCHANGE_P2P 1u     /* t1+t2 fused: the Y pass stores straight into the peers' receive buffers over NVLink */
+#define DFFT_EXCHANGE_NCCL 2u    /* Y pass packs locally, grouped ncclSend/ncclRecv (ncclAlltoAll when the library has it) */
+#define DFFT_EXCHANGE_STAGED 3u  /* reference-like: separate pack kernel + peer copies, device sync after every stage */
+#define DFFT_EXCHANGE_MASK 3u
+#define DFFT_SCALE_BACKWARD 4u   /* divide by N0*N1*N2 in the last backward pass (the `roc` variant's scale_element,
+                                    3dmpifft_roc/include/fft_mpi_3d_api.cpp:208-210); default off like 3dmpifft_opt */
+
+#define DFFT_EINVAL (-1)
+#define DFFT_ECUDA (-2)
+#define DFFT_EUNSUPPORTED (-3)
+#define DFFT_ECOMM (-4)
+#define DFFT_ENOMEM (-5)
+
+typedef struct dfft_plan_s* dfft_plan;
+typedef struct dfft_comm_s* dfft_comm;
+
+/* Bootstrap all-gather supplied by the host program in process-per-GPU mode: every rank
+ * contributes `bytes` bytes from `send`; on return `recv` holds nranks*bytes in rank order.
+ * Plays the role MPI_Comm plays in the reference (fft_mpi_3d_api.h:68,70). */
+typedef int (*dfft_allgather_fn)(void* ctx, const void* send, void* recv, size_t bytes);
+
+/* -- library ------------------------------------------------------------------------------- */
+const char* dfft_last_error(void);
+int dfft_version(void);
+/* number of supported transform lengths for a precision; fills `lengths` (may be NULL) */
+int dfft_supported_lengths(int precision, int* lengths, int max_lengths);
+
+/* -- slab bookkeeping ---------------------------------------------------------------------- */
+/* fft_mpi_init, fft_mpi_3d_api.cpp:3-39 (+ getProperDeviceNum :232-272, getDataCountForNode :274-287):
+ * shrink `wanted_devices` (clamped to the visible device count unless that is 0) so that ceil-blocks
+ * of N[0] leave no device empty, return per-device input element counts, enable peer access
+ * between the devices used.  `counts` must have room for `wanted_devices` entries. */
+int dfft_init(const long long N[3], int wanted_devices, int* total_devices, int* local_devices, long long* counts);
+/* getMaxDataCount, fft_mpi_3d_api.cpp:289-316: elements each of in/out must hold on a device */
+long long dfft_max_data_count(long long n0, long long n1, long long n2, int total_devices, int is_last_device);
+/* fft_mpi_local_size_3d (declared fft_mpi_3d_api.h:73, never defined in the reference): returns the
+ * allocation count and the slab owned by `dev_idx` before (x) and after (y) the exchange */
+long long dfft_local_size_3d(long long n0, long long n1, long long n2, int total_devices, int dev_idx,
+                             long long* local_n0, long long* local_0_start, long long* local_n1,
+                             long long* local_1_start);
+/* fft_mpi_alloc_local_memory, fft_mpi_3d_api.cpp:216-230 (64-bit count; ALLOC_CPU is pinned) */
+void* dfft_alloc_local(long long count, int flag, int precision);
+int dfft_free_local(void* ptr, int flag);
+
+/* -- communicator -------------------------------------------------------------------------- */
+/* P device-threads inside one process (the reference's multi-GPU-per-rank mode). Returns one shared
+ * handle; every participating thread passes it to dfft_plan_c2c_3d with its own dev_idx. */
+int dfft_comm_create_local(int nranks, dfft_comm* comm);
+/* One process per GPU; `allgather` is used during plan creation / teardown only. */
+int dfft_comm_create_bootstrap(int rank, int nranks, dfft_allgather_fn allgather, void* ctx, dfft_comm* comm);
+int dfft_comm_destroy(dfft_comm comm);
+
+/* -- plan / execute ------------------------------------------------------------------------ */
+/* fft_mpi_plan_dft_c2c_3d, fft_mpi_3d_api.cpp:41-141.  Same ownership rules: `in`/`out` are the
+ * caller's device buffers of dfft_max_data_count() elements; out == NULL or out == in means in
+ * place; the plan owns bufferDev1 and copies `in` into it at creation (api.cpp:76-77); bufferDev2
+ * aliases `out`.  Execute never re-reads `in`: refill bufferDev1 (dfft_plan_buffers) to transform new
+ * data, exactly like the reference driver does (fftSpeed3d_c2c.cpp:78).
+ * `comm` may be NULL when total_devices == 1.  `dev_idx` is this device's global index (= rank).
+ * The CUDA device current at the call is the plan's device. */
+int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* in, void* out, dfft_comm comm, int dev_idx,
+                     int total_devices, int direction, int precision, unsigned flags, dfft_plan* plan);
+/* fft_mpi_execute_dft_3d_c2c, fft_mpi_3d_api.cpp:181-214.  Asynchronous on the plan's stream;
+ * dfft_synchronize() or dfft_get_timings() waits.  Result in bufferDev2 (= out). */
+int dfft_execute(dfft_plan plan);
+int dfft_synchronize(dfft_plan plan);
+/* One reference stage at a time (0: t0 fftZY, 1: t1 pack, 2: t2 all-to-all, 3: t3 fftX, in the
+ * order the plan's direction executes them), leaving bufferDev1/bufferDev2 exactly as the reference
+ * leaves them after that stage.  Requires a plan created with DFFT_EXCHANGE_STAGED.  Synchronous. */
+int dfft_execute_stage(dfft_plan plan, int stage);
+/* Host-buffer entry: copies `host_in` (input-slab elements) to bufferDev1, executes, copies the
+ * result slab to `host_out`; copies are on the plan's stream (pinned buffers overlap). Synchronous. */
+int dfft_execute_host(dfft_plan plan, const void* host_in, void* host_out);
+/* milliseconds of the last execute: t[0..3] = t0,t1,t2,t3 as the reference prints them
+ * (api.cpp:201; fused stages report 0 for t1 and the *exposed* wait for t2), t[4] = total. */
+int dfft_get_timings(dfft_plan plan, double t_ms[5]);
+/* bufferDev1 / bufferDev2 of the plan (fft_mpi_3d_api.h:24; the driver writes into bufferDev1) */
+int dfft_plan_buffers(dfft_plan plan, void** buffer1, void** buffer2);
+/* element counts of this device's input slab and output slab */
+int dfft_plan_counts(dfft_plan plan, long long* in_count, long long* out_count, long long* max_count);
+/* kernels launched by the last execute (for bench.py's gpu_launches) */
+int dfft_plan_launches(dfft_plan plan);
+/* which exchange the plan resolved to (DFFT_EXCHANGE_*) */
+int dfft_plan_exchange(dfft_plan plan);
+/* the stream the plan launches on (a cudaStream_t), so callers can time with events on it */
+void* dfft_plan_stream(dfft_plan plan);
+/* fft_mpi_destroy_plan, fft_mpi_3d_api.cpp:143-179 (collective when P > 1) */
+int dfft_destroy(dfft_plan plan);
+/* fft_mpi_cleanup (declared fft_mpi_3d_api.h:69, never defined in the reference) */
+int dfft_cleanup(void);
+
+/* convenience for hosts without a CUDA runtime binding (tests): synchronous cudaMemcpy,
+ * kind 1 = host->device, 2 = device->host, 0 = default (UVA) */
+int dfft_memcpy(void* dst, const void* src, size_t bytes, int kind);
+
+/* -- batched local transforms (the templateFFT engine surface, opt/include/templateFFT.h:361-365:
+ *    initializeFFT / launchFFTKernel on a contiguous or strided axis), used by per-axis parity tests
+ *    and the batched 1-D benchmark.  Transforms `nlines` lines of length n in place:
+ *    line l starts at data + (l / inner) * outer_dist + (l % inner) * inner_dist (in elements),
+ *    points are `stride` elements apart.  Supported shapes: stride == 1 (inner_dist == n), or
+ *    stride > 1 with inner_dist == 1 (columns of a row-major matrix).  Synchronous. */
+int dfft_fft_lines(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
+                   long long outer_dist, int direction, int precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFFT_H */

@@ -1,0 +1,205 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path through the C ABI versus the CPU
+oracle on the same seeded inputs, the committed golden vectors, and size-independent properties at
+the BASELINE sizes.  Tolerances: fp64 relative L-inf 1e-12*log2(N) per axis / 1e-11 absolute round
+trip on U(0,1) data (heffte/heffteBenchmark/test/test_common.h:136-140); fp32 5e-4."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import distributedfft_b200 as dfft  # noqa: E402
+from oracle import BACKWARD, FORWARD, COracle, NumpySlab, SlabGeometry  # noqa: E402
+from gpu_helpers import CDT, run_slab  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def co():
+    return COracle()
+
+
+def _dev_array(a, precision):
+    npdt, tdt = CDT[precision]
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=npdt)).cuda()
+
+
+def test_library_loaded_and_gpu_present():
+    assert torch.cuda.is_available(), "these tests must run on a CUDA device"
+    assert os.path.exists(dfft.LIB_PATH)
+    assert dfft.lib().dfft_version() >= 100
+
+
+def test_golden_vectors_through_cabi():
+    """heFFTe pen-and-paper box + 11-point DFT is not a supported length (prime 11) -> the box only:
+    sizes 2,3,4 are below the kernel's minimum length except 4; check axis of length 4 and the
+    12/6/9-point engines against the same closed forms via numpy instead."""
+    with open(os.path.join(HERE, "golden", "heffte_vectors.json")) as f:
+        gold = json.load(f)
+    shape = tuple(gold["box_shape_c_order"])
+    c = lambda v: np.asarray(v)[..., 0] + 1j * np.asarray(v)[..., 1]
+    x = c(gold["box_input"]).reshape(shape)
+    ref = c(gold["box_fft_dim2_axis0"]).reshape(shape)   # transforms over the size-4 (slowest) axis, stride 6
+    t = _dev_array(x.reshape(-1), dfft.DOUBLE)
+    dfft.fft_lines(t.data_ptr(), 4, 6, 6, 6, 1, 24, FORWARD)
+    got = t.cpu().numpy().reshape(shape)
+    assert np.abs(got - ref).max() < 1e-11
+
+
+@pytest.mark.parametrize("precision", [dfft.DOUBLE, dfft.FLOAT])
+def test_every_supported_length_per_axis(co, precision):
+    """K1/K2 single-axis parity for every instantiated length, contiguous and strided, fwd + inverse."""
+    tol = 1e-12 if precision == dfft.DOUBLE else 2e-6
+    rng = np.random.default_rng(7)
+    for n in dfft.supported_lengths(precision):
+        # contiguous: 37 lines (ragged versus the tile width)
+        a = rng.standard_normal((37, n)) + 1j * rng.standard_normal((37, n))
+        a = a.astype(CDT[precision][0])
+        for direction, sign in ((FORWARD, -1), (BACKWARD, +1)):
+            ref = co.fft_axis(a.astype(np.complex128), 1, sign)
+            t = _dev_array(a.reshape(-1), precision)
+            dfft.fft_lines(t.data_ptr(), n, 1, 37, 37, n, 37 * n, direction, precision)
+            got = t.cpu().numpy().reshape(37, n)
+            err = np.abs(got - ref).max() / np.abs(ref).max()
+            assert err <= tol * max(1.0, np.log2(n)), (n, "contig", direction, err)
+        # strided: 3 matrices of n rows x 21 columns (21 is ragged for every tile width)
+        b = rng.standard_normal((3, n, 21)) + 1j * rng.standard_normal((3, n, 21))
+        b = b.astype(CDT[precision][0])
+        for direction, sign in ((FORWARD, -1), (BACKWARD, +1)):
+            ref = co.fft_axis(b.astype(np.complex128), 1, sign)
+            t = _dev_array(b.reshape(-1), precision)
+            dfft.fft_lines(t.data_ptr(), n, 21, 3 * 21, 21, 1, n * 21, direction, precision)
+            got = t.cpu().numpy().reshape(3, n, 21)
+            err = np.abs(got - ref).max() / np.abs(ref).max()
+            assert err <= tol * max(1.0, np.log2(n)), (n, "strided", direction, err)
+
+
+SHAPES_1GPU = [(64, 64, 64), (8, 16, 32), (12, 10, 24), (96, 48, 64), (128, 100, 6), (9, 125, 49)]
+
+
+@pytest.mark.parametrize("n0,n1,n2", SHAPES_1GPU)
+def test_single_gpu_forward_backward_vs_oracle(co, n0, n1, n2):
+    """BASELINE config class 2 (1 GPU, no all-to-all) on oracle-sized cubes: forward output layout
+    [y][z][x] and values equal the oracle's; backward returns N^3 * input (unnormalised)."""
+    rng = np.random.default_rng(n0 * 7 + n1)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    g = SlabGeometry(n0, n1, n2, 1)
+    b1 = [A.reshape(-1).copy()]; b2 = [np.zeros_like(b1[0])]
+    co.slab_execute(g, b1, b2, FORWARD)
+    res = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)])
+    scale = np.abs(b2[0]).max()
+    assert np.abs(res[0]["buf2"] - b2[0]).max() <= 1e-12 * np.log2(n0 * n1 * n2) * scale
+    assert res[0]["launches"] == 3
+    # backward from the oracle's forward output
+    c1 = [b2[0].copy()]; c2 = [np.zeros_like(c1[0])]
+    co.slab_execute(g, c1, c2, BACKWARD)
+    resb = run_slab(n0, n1, n2, 1, BACKWARD, [b2[0]])
+    assert np.abs(resb[0]["buf2"] - c2[0]).max() <= 1e-12 * np.log2(n0 * n1 * n2) * np.abs(c2[0]).max()
+    assert np.abs(resb[0]["buf2"] / (n0 * n1 * n2) - A.reshape(-1)).max() <= 1e-11
+
+
+def test_single_gpu_float32(co):
+    n0, n1, n2 = 48, 96, 64
+    rng = np.random.default_rng(5)
+    A = (rng.random((n0, n1, n2)) + 1j * rng.random((n0, n1, n2))).astype(np.complex64)
+    ref = np.fft.fftn(A.astype(np.complex128)).transpose(1, 2, 0).reshape(-1)
+    res = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)], precision=dfft.FLOAT)
+    assert np.abs(res[0]["buf2"] - ref).max() / np.abs(ref).max() <= 5e-6
+    back = run_slab(n0, n1, n2, 1, BACKWARD, [res[0]["buf2"]], precision=dfft.FLOAT)
+    assert np.abs(back[0]["buf2"] / (n0 * n1 * n2) - A.reshape(-1)).max() <= 5e-4
+
+
+def test_inplace_and_scale_flag(co):
+    n0, n1, n2 = 32, 16, 64
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    ref = np.fft.fftn(A).transpose(1, 2, 0).reshape(-1)
+    res = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)], inplace=True)
+    assert np.abs(res[0]["buf2"] - ref).max() <= 1e-11 * np.abs(ref).max()
+    back = run_slab(n0, n1, n2, 1, BACKWARD, [ref], flags=dfft.SCALE_BACKWARD)
+    assert np.abs(back[0]["buf2"] - A.reshape(-1)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("n0,n1,n2", [(16, 8, 32), (12, 10, 24)])
+def test_staged_mode_matches_reference_stage_boundaries(co, n0, n1, n2):
+    """dfft_execute_stage leaves bufferDev1/2 as the reference leaves them after t0,t1,t2,t3."""
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    g = SlabGeometry(n0, n1, n2, 1)
+    res = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)], flags=dfft.EXCHANGE_STAGED, stages=[0, 1, 2, 3])
+    for s in range(4):
+        o1 = [A.reshape(-1).copy()]; o2 = [np.zeros_like(o1[0])]
+        co.slab_execute(g, o1, o2, FORWARD, s)
+        d1, d2 = res[0]["stages"][s]
+        scale = max(np.abs(o1[0]).max(), 1.0)
+        assert np.abs(d1 - o1[0]).max() <= 1e-12 * 12 * scale, s
+        if s >= 1:
+            assert np.abs(d2 - o2[0]).max() <= 1e-12 * 12 * scale, s
+
+
+def test_plan_semantics_snapshot_and_reexecute():
+    """Plan creation snapshots `in` into bufferDev1 (api.cpp:77); execute never re-reads `in`;
+    the forward Z/Y passes run in place on bufferDev1, so a second execute transforms the
+    intermediate (the reference driver therefore refills bufferDev1, fftSpeed3d_c2c.cpp:78)."""
+    n = 16
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((n, n, n)) + 1j * rng.standard_normal((n, n, n))
+    ref = np.fft.fftn(A).transpose(1, 2, 0).reshape(-1)
+    res = run_slab(n, n, n, 1, FORWARD, [A.reshape(-1)], repeat=3)
+    assert np.abs(res[0]["buf2"] - ref).max() <= 1e-11 * np.abs(ref).max()
+    t = res[0]["timings"]
+    assert len(t) == 5 and t[1] == 0.0 and abs(t[4] - (t[0] + t[2] + t[3])) < 1e-9
+
+
+def test_error_behaviour():
+    with pytest.raises(dfft.DfftError):
+        dfft.fft_mpi_plan_dft_c2c_3d(17, 16, 16, 1, 2, None, 0, 1, FORWARD)      # unsupported length
+    with pytest.raises(dfft.DfftError):
+        dfft.fft_mpi_plan_dft_c2c_3d(16, 16, 16, 1, 2, None, 0, 1, 5)            # bad direction
+    with pytest.raises(dfft.DfftError):
+        dfft.fft_mpi_plan_dft_c2c_3d(16, 16, 16, 1, 2, None, 0, 2, FORWARD)      # P=2 without a communicator
+    with pytest.raises(dfft.DfftError):
+        dfft.fft_mpi_alloc_local_memory(16, 7)                                    # bad flag ("Fail to allocate memory!")
+
+
+def test_baseline_512_cube_properties_and_roundtrip(co):
+    """BASELINE config 2 at full size (512^3 double, 1 GPU): driver ramp input round trip with the
+    driver's metric (fftSpeed3d_c2c.cpp:61-63, 84-91) <= 1e-11, Parseval, and the spectrum of the
+    ramp's DC/plane structure; plus exact comparison of 4 output y-planes with the oracle's 1-D engine."""
+    n = 512
+    n3 = n ** 3
+    cdt = torch.complex128
+    dev = torch.device("cuda", 0)
+    idx = torch.arange(n3, dtype=torch.float64, device=dev)
+    tin = torch.complex(idx, idx)
+    del idx
+    tout = torch.empty(n3, dtype=cdt, device=dev)
+    plan = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tin.data_ptr(), tout.data_ptr(), None, 0, 1, FORWARD)
+    plan.execute(); plan.synchronize()
+    t = plan.timings()
+    # Parseval: sum |X|^2 = N^3 sum |x|^2
+    e_in = float((tin.real.double() ** 2 + tin.imag.double() ** 2).sum())
+    e_out = float((tout.real ** 2 + tout.imag ** 2).sum())
+    assert abs(e_out / (n3 * e_in) - 1.0) < 1e-12
+    # DC bin = sum of inputs = (1+i) * n3 (n3-1)/2 ; forward output layout [y][z][x]
+    dc = complex(tout[0].item())
+    exact = n3 * (n3 - 1) / 2
+    assert abs(dc.real - exact) / exact < 1e-13 and abs(dc.imag - exact) / exact < 1e-13
+    # ramp separability: X[kx,0,0] (x line of y=z=0) = n^2 * n^2 * DFT_n(ramp_x) for kx != 0
+    line = tout[:n].cpu().numpy()
+    kx = np.arange(1, n)
+    expect = (1 + 1j) * (n * n) * (n * n) * (-n / 2 + 0.5j * n / np.tan(np.pi * kx / n))
+    assert np.abs(line[1:] - expect).max() / np.abs(expect).max() < 1e-11
+    planb = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tout.data_ptr(), tin.data_ptr(), None, 0, 1, BACKWARD)
+    planb.execute(); planb.synchronize()
+    idx = torch.arange(n3, dtype=torch.float64, device=dev)
+    er = (tin.real / n3 - idx).abs().max().item()
+    ei = (tin.imag / n3 - idx).abs().max().item()
+    drv_metric = np.hypot(er, ei) / 1e7
+    assert drv_metric <= 1e-11, drv_metric
+    plan.destroy(); planb.destroy()
+    assert t[4] > 0
