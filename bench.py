@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: forward 3-D C2C FFT, GFlops/s = 5 N^3 log2(N^3) / t
+(3dmpifft_opt/fftSpeed3d_c2c.cpp:126-128), per-stage t0..t3 ms, HBM-roofline fraction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl dfft|reference] [--size 512] [--precision double]
+
+A "step" is one forward transform of the synthetic N^3 cube (BASELINE.json configs[1]: 512^3 double on
+1 GPU; the same cube sharded over N GPUs = strong scaling).  N > 1 runs one process per GPU under
+torchrun; torch.distributed is plumbing only (bootstrap of IPC handles, barrier, max-over-ranks).
+
+`--impl reference` times the CPU oracle port of the reference path (oracle/oracle_fft.c, OpenMP on all
+host cores): the reference's own implementation needs HIP/rocFFT/MPI and cannot be built here.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def flops(n0, n1, n2):
+    n3 = float(n0) * n1 * n2
+    return 5.0 * n3 * math.log2(n3)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference path)
+# ----------------------------------------------------------------------------------------------
+def cpu_forward_rate(n, budget_s=20.0, steps=None, warmup=0):
+    """Times the oracle's slab pipeline on the host cores.  Full n^3 transforms when one fits the
+    budget, otherwise the share of device 0 of an 8-way slab decomposition (1/8 of the work: 64
+    planes of 2-D FFT + pack + its 64 y-rows of X lines) scaled by 8.  Returns a dict."""
+    import numpy as np
+    from oracle import FORWARD, COracle, SlabGeometry
+
+    co = COracle()
+    threads = co.num_threads()
+    g = SlabGeometry(n, n, n, 1)
+    a = np.zeros(n ** 3, dtype=np.complex128)
+    co.fill_minstd(a[: min(a.size, 1 << 22)], 4242)   # U(0,1) heFFTe-style input (values do not affect FFT time)
+    a[1 << 22:] = 0.5
+    b1 = [a]
+    b2 = [np.zeros_like(a)]
+    t = time.perf_counter(); co.slab_execute(g, b1, b2, FORWARD); first = time.perf_counter() - t
+    if steps:   # reference arm: K timed + W warm-up steps must end within a few minutes
+        full = first * (steps + warmup) <= 150.0
+    else:       # cpu_baseline leg: about budget_s of CPU work
+        full = first <= budget_s / 2
+    times = []
+    if full:
+        reps = steps if steps else max(1, min(5, int(budget_s / max(first, 1e-3))))
+        for _ in range(warmup):
+            co.slab_execute(g, b1, b2, FORWARD)
+        for _ in range(reps):
+            t = time.perf_counter(); co.slab_execute(g, b1, b2, FORWARD); times.append(time.perf_counter() - t)
+        sample = f"{reps} full {n}^3 forward transforms (t0 2-D FFT per plane, t1 pack, t2 self copy, t3 transpose + X FFT)"
+        scale = 1.0
+    else:
+        P = 8
+        g8 = SlabGeometry(n, n, n, P)
+        # only device 0's buffers take part: stage functions are called through slab_execute on a
+        # 1-device geometry of the slab shape (n/8 planes for t0/t1; n/8 y-rows for t3)
+        xs = n // P
+        slab = SlabGeometry(xs, n, n, 1)
+        reps = steps if steps else max(1, min(20, int(budget_s / max(first / P, 1e-3))))
+        c1 = [a[: xs * n * n]]; c2 = [b2[0][: xs * n * n]]
+        lib = co.lib
+        for it in range(warmup + reps):
+            t = time.perf_counter()
+            lib.oracle_stage_fftZY(c1[0].ctypes.data, xs, n, n, FORWARD)
+            lib.oracle_stage_pack(c1[0].ctypes.data, c2[0].ctypes.data, xs, n, n, 1, FORWARD)
+            lib.oracle_stage_fftX(c2[0].ctypes.data, c1[0].ctypes.data, n, xs, n, FORWARD)
+            if it >= warmup:
+                times.append((time.perf_counter() - t) * P)
+        sample = (f"{reps} x the share of 1 of {P} slab devices of the {n}^3 forward transform "
+                  f"({xs} planes of t0/t1 + {xs}x{n} X lines of t3), time scaled by {P}")
+        scale = float(P)
+        del g8, slab
+    best = min(times)
+    mean = sum(times) / len(times)
+    return {"best_s": best, "mean_s": mean, "threads": threads, "sample": sample, "scale": scale, "times": times}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.size
+    r = cpu_forward_rate(n, budget_s=20.0, steps=args.steps, warmup=args.warmup)
+    ms = r["mean_s"] * 1e3
+    val = flops(n, n, n) * 1e-9 / r["mean_s"]
+    line = {
+        "impl": "reference", "metric": "3D C2C forward FFT GFlops/s (5*N^3*log2(N^3)/t)", "value": val, "unit": "GFlops/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n}x{n}x{n} C2C double forward, CPU oracle port of the reference path (no GPU)",
+                   "host_threads": r["threads"]},
+        "cpu_baseline": {"value": val, "unit": "GFlops/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": val, "unit": "GFlops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_dfft_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import distributedfft_b200 as dfft
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun --nproc-per-node N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the dfft arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    boot = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        boot = dist.new_group(backend="gloo")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.size
+    prec = dfft.DOUBLE if args.precision == "double" else dfft.FLOAT
+    tdt = torch.complex128 if prec == dfft.DOUBLE else torch.complex64
+    esz = 16 if prec == dfft.DOUBLE else 8
+    P = world
+    tot, _, counts = dfft.fft_mpi_init([n, n, n], P)
+    if tot != P:
+        raise SystemExit(f"{n}^3 cannot use {P} devices (library suggests {tot})")
+    maxc = dfft.getMaxDataCount(n, n, n, P, rank == P - 1)
+
+    comm = None
+    if P > 1:
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b, group=boot)
+            return out
+        comm = dfft.BootstrapComm(rank, P, allgather)
+
+    # synthetic input: U(0,1) real/imag, seeded per rank; inputs (2 GiB at 512^3) are larger than L2 (126 MB)
+    gen = torch.Generator(device=dev); gen.manual_seed(4242 + rank)
+    tin = torch.empty(maxc, dtype=tdt, device=dev)
+    torch.view_as_real(tin).uniform_(0.0, 1.0, generator=gen)
+    tout = torch.empty(maxc, dtype=tdt, device=dev)
+    torch.cuda.synchronize(dev)
+    flags = {"auto": dfft.EXCHANGE_AUTO, "p2p": dfft.EXCHANGE_P2P, "nccl": dfft.EXCHANGE_NCCL}[args.exchange]
+    plan = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tin.data_ptr(), tout.data_ptr(), comm, rank, P, dfft.FORWARD, prec, flags)
+    stream = torch.cuda.ExternalStream(plan.stream, device=dev)
+
+    for _ in range(max(args.warmup, 3)):
+        plan.execute()
+    plan.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.execute()
+    e1.record(stream)
+    plan.synchronize()
+    barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = total_ms / args.steps
+    stage = [max_over_ranks(x) for x in plan.timings()]
+    passes = [max_over_ranks(x) for x in plan.pass_timings()]
+    launches = plan.launches * args.steps
+
+    # per-pass averages over a few more executes (events bracket each launch on the plan's stream)
+    acc = [0.0, 0.0, 0.0]
+    reps = 5
+    for _ in range(reps):
+        plan.execute()
+        pt = plan.pass_timings()
+        acc = [a + b for a, b in zip(acc, pt)]
+    passes_avg = [max_over_ranks(a / reps) for a in acc]
+
+    # e2e: host buffers through the C ABI (H2D + transform + D2H inside the timed region)
+    in_count, out_count = plan.in_count, plan.out_count
+    h_in = dfft.fft_mpi_alloc_local_memory(in_count, dfft.ALLOC_CPU, prec)
+    h_out = dfft.fft_mpi_alloc_local_memory(out_count, dfft.ALLOC_CPU, prec)
+    dfft.memcpy_dtoh(h_in, tin.data_ptr(), in_count * esz)
+    e2e_steps = max(2, min(args.steps, 8))
+    plan.execute_host(h_in, h_out)   # warm-up (page-locks, first touch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.execute_host(h_in, h_out)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    sampler.stop()
+    clocks = sampler.summary()
+
+    F = flops(n, n, n)
+    value = F * 1e-9 / (ms_per_step * 1e-3)
+    M = float(n) ** 3 / P
+    peak, peak_src = measured_peak()
+    names = ["Z pass (contiguous, fft_tile_kernel MAP_T)", "Y pass (strided + fused pack, fft_tile_kernel MAP_C)",
+             "X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)"]
+    dom = max(range(3), key=lambda i: passes_avg[i])
+    alg_bytes = 2.0 * esz * M                       # one read + one write of the local slab per pass
+    achieved = alg_bytes / (passes_avg[dom] * 1e-3) * 1e-9
+    traffic = {512: 4.24e9}.get(n) if P == 1 and prec == dfft.DOUBLE else None   # ncu dram read+write per launch (profiles/)
+    transform_bytes = (6.0 + (2.0 if (P > 1 and plan.exchange == dfft.EXCHANGE_NCCL) else 0.0)) * esz * M
+    line = {
+        "metric": "3D C2C forward FFT GFlops/s (5*N^3*log2(N^3)/t)", "value": value, "unit": "GFlops/s",
+        "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if prec == dfft.DOUBLE else "f32", "data": "synthetic",
+        "config": {"workload": f"{n}x{n}x{n} C2C {args.precision} forward, slab decomposition over {P} GPU(s)",
+                   "exchange": {1: "p2p-fused", 2: "nccl", 3: "staged"}[plan.exchange] if P > 1 else "none",
+                   "l2": "inputs (%.2f GiB per GPU) exceed the 126 MB L2; no flush needed" % (M * esz / 2 ** 30),
+                   "parallelism": f"slab{P}"},
+        "stage_ms": {"t0": stage[0], "t1": stage[1], "t2": stage[2], "t3": stage[3], "total": stage[4]},
+        "pass_ms": {"z": passes_avg[0], "y": passes_avg[1], "x": passes_avg[2]},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                     "peak_source": peak_src,
+                     "transform": {"achieved": transform_bytes / (ms_per_step * 1e-3) * 1e-9,
+                                   "frac": transform_bytes / (ms_per_step * 1e-3) * 1e-9 / peak,
+                                   "algorithmic_bytes": transform_bytes}},
+        "e2e": {"value": F * 1e-9 / e2e_s, "unit": "GFlops/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(in_count * esz), "d2h_bytes_per_step": int(out_count * esz), "steps": e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if P == 1 and rank == 0 and not args.no_cpu:
+        n_cpu = n
+        r = cpu_forward_rate(n_cpu, budget_s=15.0)
+        line["cpu_baseline"] = {"value": flops(n_cpu, n_cpu, n_cpu) * 1e-9 / r["best_s"], "unit": "GFlops/s", "cores": r["threads"],
+                                "kind": "port", "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    dfft.lib().dfft_free_local(h_in, dfft.ALLOC_CPU)
+    dfft.lib().dfft_free_local(h_out, dfft.ALLOC_CPU)
+    plan.destroy()
+    if comm is not None:
+        comm.destroy()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="dfft", choices=["dfft", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--precision", default="double", choices=["double", "float"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_dfft_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -72,6 +72,7 @@ def lib():
     L.dfft_execute_stage.argtypes = [vp, i]
     L.dfft_execute_host.argtypes = [vp, vp, vp]
     L.dfft_get_timings.argtypes = [vp, P(ctypes.c_double)]
+    L.dfft_get_pass_timings.argtypes = [vp, P(ctypes.c_double)]
     L.dfft_plan_buffers.argtypes = [vp, P(vp), P(vp)]
     L.dfft_plan_counts.argtypes = [vp, P(ll), P(ll), P(ll)]
     L.dfft_plan_stream.argtypes = [vp]
@@ -199,6 +200,11 @@ class Plan:
     def timings(self):
         t = (ctypes.c_double * 5)()
         _check(lib().dfft_get_timings(self.handle, t), "dfft_get_timings")
+        return list(t)
+
+    def pass_timings(self):
+        t = (ctypes.c_double * 3)()
+        _check(lib().dfft_get_pass_timings(self.handle, t), "dfft_get_pass_timings")
         return list(t)
 
     @property

@@ -336,15 +336,17 @@ struct dfft_plan_s {
     int xmode = DFFT_EXCHANGE_P2P;
     size_t esz = 16;
     long long n0l = 0, n1l = 0, in_count = 0, out_count = 0, max_count = 0;
-    void *in = nullptr, *out = nullptr, *buf1 = nullptr, *buf2 = nullptr, *recv = nullptr;
+    void *in = nullptr, *out = nullptr, *buf1 = nullptr, *buf2 = nullptr;
+    void* work = nullptr;   // plan-owned scratch / receive buffer: keeps bufferDev1 intact so execute is repeatable
     bool inplace = false;
     const SizeEntry *ez = nullptr, *ey = nullptr, *ex = nullptr;   // axes N2 (Z), N1 (Y), N0 (X)
     void *lut_z = nullptr, *lut_y = nullptr, *lut_x = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // per pass (Z, Y, X) brackets
     dfft_comm comm = nullptr;
     // p2p
-    std::vector<void*> peer_recv, peer_buf1;
+    std::vector<void*> peer_work, peer_buf1;
     SyncBlock* sync = nullptr;
     std::vector<SyncBlock*> peer_sync;
     std::vector<void*> ipc_opened;
@@ -432,6 +434,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     CUP(cudaMemcpy(p->buf1, in, (size_t)p->max_count * p->esz, cudaMemcpyDeviceToDevice));
     CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (auto& e : p->ev) CUP(cudaEventCreate(&e));
+    for (auto& pe : p->pev) for (auto& e : pe) CUP(cudaEventCreate(&e));
     if (precision == DFFT_DOUBLE) {
         upload_lut<double>(&p->lut_z, ez->z_nstages, ez->z_rad);
         upload_lut<double>(&p->lut_y, ey->s_nstages, ey->s_rad);
@@ -453,11 +456,11 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         else xmode = DFFT_EXCHANGE_P2P;
     }
     p->xmode = xmode;
+    if (xmode != DFFT_EXCHANGE_STAGED) CUP(cudaMalloc(&p->work, (size_t)p->max_count * p->esz));
     if (P > 1) {
         if (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_STAGED) {
             if (xmode == DFFT_EXCHANGE_P2P) {
-                CUP(cudaMalloc(&p->recv, (size_t)p->max_count * p->esz));
-                if ((rc = share_pointer(p, p->recv, p->peer_recv)) != 0) return bail(rc);
+                if ((rc = share_pointer(p, p->work, p->peer_work)) != 0) return bail(rc);
             } else {
                 if ((rc = share_pointer(p, p->buf1, p->peer_buf1)) != 0) return bail(rc);
             }
@@ -499,12 +502,13 @@ extern "C" int dfft_destroy(dfft_plan p)
     for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
     if (p->P > 1 && p->comm && !p->comm->local && !p->ipc_opened.empty()) p->comm->host_barrier(p->me);
     if (p->buf1) cudaFree(p->buf1);
-    if (p->recv) cudaFree(p->recv);
+    if (p->work) cudaFree(p->work);
     if (p->sync) cudaFree(p->sync);
     if (p->lut_z) cudaFree(p->lut_z);
     if (p->lut_y) cudaFree(p->lut_y);
     if (p->lut_x) cudaFree(p->lut_x);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& pe : p->pev) for (auto& e : pe) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaGetLastError();
     delete p;
@@ -526,19 +530,22 @@ template <typename T> struct Pass {
     static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a)
     {
         a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
+        const int axis = kind == PK_Z ? 0 : (kind == PK_Y || kind == PK_Y_CO || kind == PK_Y_CI ? 1 : 2);
+        cudaEventRecord(p->pev[axis][0], p->stream);
         cudaError_t err = e->launch[kind](&a, p->sms, p->stream);
+        cudaEventRecord(p->pev[axis][1], p->stream);
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "pass launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
     }
-    // contiguous lines of length N2 in `buf` (n0l*N1 lines), in place
-    static int z_pass(dfft_plan p, void* buf, bool scale)
+    // contiguous lines of length N2 (n0l*N1 lines), src -> dst (in place when equal)
+    static int z_pass(dfft_plan p, const void* src, void* dst, bool scale)
     {
         const Geom& g = p->g;
         TileArgs<T> a{};
         const int C = p->ez->z_C;
         const long long nlines = p->n0l * g.n1;
-        a.in = (const cx<T>*)buf; a.out = (cx<T>*)buf; a.lut = (const cx<T>*)p->lut_z;
+        a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_z;
         a.G = (int)cdiv(nlines, C); a.W = (int)std::min<long long>(nlines, 0x7fffffff); a.ntiles = a.G;
         a.ia = Affine{0, (long long)C * g.n2, g.n2, 1}; a.oa = a.ia;
         a.do_scale = scale ? 1 : 0; a.scale = (T)(1.0 / ((double)g.n0 * (double)g.n1 * (double)g.n2));
@@ -655,33 +662,36 @@ template <typename T> static int execute_fused(dfft_plan p)
     p->launches = 0;
     CU(cudaEventRecord(p->ev[0], p->stream));
     if (p->direction == DFFT_FORWARD) {
-        // t0 (+t1): Z pass in place, Y pass with the pack (and, P2P, the all-to-all) folded into its store
-        if ((rc = Pass<T>::z_pass(p, p->buf1, false))) return rc;
+        // t0 (+t1): Z pass out of place (bufferDev1 survives), Y pass with the pack (and, P2P, the
+        // all-to-all) folded into its store
         if (P == 1) {
-            if ((rc = Pass<T>::y_pass(p, p->buf1, p->buf1, 0, nullptr))) return rc;
+            if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
+            if ((rc = Pass<T>::y_pass(p, p->work, p->work, 0, nullptr))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
             CU(cudaEventRecord(p->ev[2], p->stream));
-            if ((rc = Pass<T>::x_fwd(p, p->buf1, p->buf2))) return rc;
+            if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
+            if ((rc = Pass<T>::z_pass(p, p->buf1, p->buf2, false))) return rc;
             p->epoch++;
             if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
             void* base[DFFT_MAX_CHUNKS];
-            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_recv[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
-            if ((rc = Pass<T>::y_pass(p, p->buf1, nullptr, 1, base))) return rc;
+            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
+            if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base))) return rc;
             if ((rc = flags_signal(p, true, p->epoch))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
             if ((rc = flags_wait(p, true, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
             CU(cudaEventRecord(p->ev[2], p->stream));
-            if ((rc = Pass<T>::x_fwd(p, p->recv, p->buf2))) return rc;
+            if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
             if ((rc = flags_signal(p, false, p->epoch))) return rc;
         } else {
+            if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->buf2, send_off(g, me, q, DFFT_FORWARD), p->esz);
-            if ((rc = Pass<T>::y_pass(p, p->buf1, nullptr, 1, base))) return rc;
+            if ((rc = Pass<T>::y_pass(p, p->work, nullptr, 1, base))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
-            if ((rc = nccl_exchange(p, p->buf2, p->buf1))) return rc;
+            if ((rc = nccl_exchange(p, p->buf2, p->work))) return rc;
             CU(cudaEventRecord(p->ev[2], p->stream));
-            if ((rc = Pass<T>::x_fwd(p, p->buf1, p->buf2))) return rc;
+            if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
         }
         CU(cudaEventRecord(p->ev[3], p->stream));
     } else {
@@ -695,26 +705,26 @@ template <typename T> static int execute_fused(dfft_plan p)
             p->epoch++;
             if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;
             void* base[DFFT_MAX_CHUNKS];
-            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_recv[q], recv_off(g, me, q, DFFT_BACKWARD), p->esz);
+            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_BACKWARD), p->esz);
             if ((rc = Pass<T>::x_bwd(p, p->buf1, nullptr, base))) return rc;
             if ((rc = flags_signal(p, true, p->epoch))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
             if ((rc = flags_wait(p, true, p->epoch))) return rc;
             CU(cudaEventRecord(p->ev[2], p->stream));
             void* cb[DFFT_MAX_CHUNKS];
-            for (int q = 0; q < P; q++) cb[q] = eoff(p->recv, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
+            for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
             if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
             if ((rc = flags_signal(p, false, p->epoch))) return rc;
         } else {
             if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
-            if ((rc = nccl_exchange(p, p->buf2, p->buf1))) return rc;
+            if ((rc = nccl_exchange(p, p->buf2, p->work))) return rc;
             CU(cudaEventRecord(p->ev[2], p->stream));
             void* cb[DFFT_MAX_CHUNKS];
-            for (int q = 0; q < P; q++) cb[q] = eoff(p->buf1, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
+            for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
             if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
         }
-        if ((rc = Pass<T>::z_pass(p, p->buf2, scale))) return rc;
+        if ((rc = Pass<T>::z_pass(p, p->buf2, p->buf2, scale))) return rc;
         CU(cudaEventRecord(p->ev[3], p->stream));
     }
     p->timed = true;
@@ -732,11 +742,11 @@ template <typename T> static int execute_stage(dfft_plan p, int stage)
     if (sid == 0) {          // fftZY
         void* buf = dir == DFFT_FORWARD ? p->buf1 : p->buf2;
         if (dir == DFFT_FORWARD) {
-            if ((rc = Pass<T>::z_pass(p, buf, false))) return rc;
+            if ((rc = Pass<T>::z_pass(p, buf, buf, false))) return rc;
             if ((rc = Pass<T>::y_pass(p, buf, buf, 0, nullptr))) return rc;
         } else {
             if ((rc = Pass<T>::y_pass(p, buf, buf, 0, nullptr))) return rc;
-            if ((rc = Pass<T>::z_pass(p, buf, (p->flags & DFFT_SCALE_BACKWARD) != 0))) return rc;
+            if ((rc = Pass<T>::z_pass(p, buf, buf, (p->flags & DFFT_SCALE_BACKWARD) != 0))) return rc;
         }
     } else if (sid == 1) {   // localTransposeUneven
         cudaError_t e = launch_pack_rows(p->buf1, p->buf2, (int)p->esz, p->n0l, g.n1, g.n2, P, dir == DFFT_FORWARD, p->sms, p->stream);
@@ -820,6 +830,20 @@ extern "C" int dfft_get_timings(dfft_plan p, double t[5])
         else { t[3] = a; t[2] = b; t[1] = 0; t[0] = c; }
     }
     t[4] = t[0] + t[1] + t[2] + t[3];
+    return 0;
+}
+
+extern "C" int dfft_get_pass_timings(dfft_plan p, double t[3])
+{
+    if (!p || !t) return fail(DFFT_EINVAL, "bad arguments");
+    if (!p->timed) return fail(DFFT_EINVAL, "no execute to time yet");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    for (int a = 0; a < 3; a++) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, p->pev[a][0], p->pev[a][1]));
+        t[a] = ms;
+    }
     return 0;
 }
 

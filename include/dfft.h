@@ -116,6 +116,8 @@ int dfft_execute_host(dfft_plan plan, const void* host_in, void* host_out);
 /* milliseconds of the last execute: t[0..3] = t0,t1,t2,t3 as the reference prints them
  * (api.cpp:201; fused stages report 0 for t1 and the *exposed* wait for t2), t[4] = total. */
 int dfft_get_timings(dfft_plan plan, double t_ms[5]);
+/* milliseconds of the Z, Y and X pass kernels of the last execute (CUDA events around each launch) */
+int dfft_get_pass_timings(dfft_plan plan, double t_ms[3]);
 /* bufferDev1 / bufferDev2 of the plan (fft_mpi_3d_api.h:24; the driver writes into bufferDev1) */
 int dfft_plan_buffers(dfft_plan plan, void** buffer1, void** buffer2);
 /* element counts of this device's input slab and output slab */

@@ -214,6 +214,11 @@ class COracle:
         L.oracle_roundtrip_error.argtypes = [vp, vp, i64, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
         L.oracle_roundtrip_error.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_stage_fftZY.argtypes = [vp, i64, i64, i64, ctypes.c_int]
+        L.oracle_stage_pack.argtypes = [vp, vp, i64, i64, i64, ctypes.c_int, ctypes.c_int]
+        L.oracle_stage_fftX.argtypes = [vp, vp, i64, i64, i64, ctypes.c_int]
+        for f in (L.oracle_stage_fftZY, L.oracle_stage_pack, L.oracle_stage_fftX):
+            f.restype = None
 
     def radix_schedule(self, n):
         r = (ctypes.c_int * 32)()

@@ -79,18 +79,17 @@ static inline cplx cmul(cplx a, cplx b)
  * out[(j-k)*r + k + m*ns].  `root` holds e^{sign 2 pi i q / r} for the small DFT,
  * `tw` the n-point table e^{sign 2 pi i q / n}. */
 static void stockham_stage(const cplx *in, cplx *out, int n, int r, int ns,
-                           const cplx *tw, const cplx *root)
+                           const cplx *stw, const cplx *root)
 {
+    /* stw[k*(r-1) + (m-1)] = e^{sign 2 pi i k m / (ns r)}: the per-stage LUT of the reference
+       (templateFFT.cpp:5121-5141), so the inner loop has no index arithmetic beyond k */
     const int nb = n / r;            /* butterflies */
-    const int tstep = n / (ns * r);  /* table step for angle 2 pi k m /(ns r) */
     cplx v[13], y[13];
-    for (int j = 0; j < nb; j++) {
-        const int k = j % ns;
-        for (int m = 0; m < r; m++) {
-            cplx x = in[j + m * nb];
-            if (k != 0 && m != 0) x = cmul(x, tw[((i64)k * m * tstep) % n]);
-            v[m] = x;
-        }
+    int k = 0;
+    for (int j = 0; j < nb; j++, k = (k + 1 == ns) ? 0 : k + 1) {
+        v[0] = in[j];
+        if (k == 0) for (int m = 1; m < r; m++) v[m] = in[j + m * nb];
+        else { const cplx *w = stw + (size_t)k * (r - 1); for (int m = 1; m < r; m++) v[m] = cmul(in[j + m * nb], w[m - 1]); }
         if (r == 2) {
             y[0].re = v[0].re + v[1].re; y[0].im = v[0].im + v[1].im;
             y[1].re = v[0].re - v[1].re; y[1].im = v[0].im - v[1].im;
@@ -142,8 +141,9 @@ static void stockham_stage(const cplx *in, cplx *out, int n, int r, int ns,
 
 typedef struct {
     int n, nstages, radix[32], sign;
-    cplx *tw;          /* n entries */
+    cplx *tw;          /* n entries (plain-DFT fallback only) */
     cplx *root[32];    /* per stage r entries */
+    cplx *stw[32];     /* per stage ns*(r-1) twiddles */
 } fft_plan1d;
 
 static int plan1d_init(fft_plan1d *p, int n, int sign)
@@ -152,10 +152,15 @@ static int plan1d_init(fft_plan1d *p, int n, int sign)
     p->nstages = oracle_radix_schedule(n, p->radix);
     p->tw = (cplx *)malloc(sizeof(cplx) * (size_t)(n > 0 ? n : 1));
     for (int k = 0; k < n; k++) p->tw[k] = twiddle(k, n, sign);
+    int ns = 1;
     for (int s = 0; s < p->nstages; s++) {
         int r = p->radix[s];
         p->root[s] = (cplx *)malloc(sizeof(cplx) * (size_t)r);
         for (int q = 0; q < r; q++) p->root[s][q] = twiddle(q, r, sign);
+        p->stw[s] = (cplx *)malloc(sizeof(cplx) * (size_t)ns * (size_t)(r - 1));
+        for (int k = 0; k < ns; k++)
+            for (int m = 1; m < r; m++) p->stw[s][(size_t)k * (r - 1) + (m - 1)] = twiddle((i64)k * m, (i64)ns * r, sign);
+        ns *= r;
     }
     return p->nstages;
 }
@@ -163,7 +168,7 @@ static int plan1d_init(fft_plan1d *p, int n, int sign)
 static void plan1d_free(fft_plan1d *p)
 {
     free(p->tw);
-    for (int s = 0; s < p->nstages; s++) free(p->root[s]);
+    for (int s = 0; s < p->nstages; s++) { free(p->root[s]); free(p->stw[s]); }
 }
 
 /* transform one contiguous line in `a` (result returned in `a`), `b` is scratch of n */
@@ -183,7 +188,7 @@ static void fft_line(const fft_plan1d *p, cplx *a, cplx *b)
     cplx *src = a, *dst = b;
     int ns = 1;
     for (int s = 0; s < p->nstages; s++) {
-        stockham_stage(src, dst, n, p->radix[s], ns, p->tw, p->root[s]);
+        stockham_stage(src, dst, n, p->radix[s], ns, p->stw[s], p->root[s]);
         ns *= p->radix[s];
         cplx *t = src; src = dst; dst = t;
     }
@@ -198,16 +203,32 @@ void oracle_fft_batch(cplx *base, int n, i64 stride, i64 nlines, i64 inner, i64 
 {
     fft_plan1d plan;
     plan1d_init(&plan, n, sign);
+    enum { BLK = 8 };   /* columns gathered together: 8 complex doubles = two cache lines per row */
 #pragma omp parallel
     {
-        cplx *a = (cplx *)malloc(sizeof(cplx) * (size_t)n);
+        cplx *a = (cplx *)malloc(sizeof(cplx) * (size_t)n * BLK);
         cplx *b = (cplx *)malloc(sizeof(cplx) * (size_t)n);
+        if (stride == 1) {
 #pragma omp for schedule(static)
-        for (i64 l = 0; l < nlines; l++) {
-            cplx *p0 = base + (l / inner) * outer_dist + (l % inner) * inner_dist;
-            if (stride == 1) {
-                fft_line(&plan, p0, b);
-            } else {
+            for (i64 l = 0; l < nlines; l++)
+                fft_line(&plan, base + (l / inner) * outer_dist + (l % inner) * inner_dist, b);
+        } else if (inner_dist == 1) {
+            const i64 nblk = (inner + BLK - 1) / BLK, groups = nlines / inner;
+#pragma omp for schedule(static)
+            for (i64 w = 0; w < groups * nblk; w++) {
+                const i64 gI = w / nblk, c0 = (w % nblk) * BLK;
+                const int nc = (int)((inner - c0) < BLK ? (inner - c0) : BLK);
+                cplx *p0 = base + gI * outer_dist + c0;
+                for (int i = 0; i < n; i++)
+                    for (int c = 0; c < nc; c++) a[(size_t)c * n + i] = p0[(i64)i * stride + c];
+                for (int c = 0; c < nc; c++) fft_line(&plan, a + (size_t)c * n, b);
+                for (int i = 0; i < n; i++)
+                    for (int c = 0; c < nc; c++) p0[(i64)i * stride + c] = a[(size_t)c * n + i];
+            }
+        } else {
+#pragma omp for schedule(static)
+            for (i64 l = 0; l < nlines; l++) {
+                cplx *p0 = base + (l / inner) * outer_dist + (l % inner) * inner_dist;
                 for (int i = 0; i < n; i++) a[i] = p0[(i64)i * stride];
                 fft_line(&plan, a, b);
                 for (int i = 0; i < n; i++) p0[(i64)i * stride] = a[i];
@@ -341,15 +362,21 @@ void oracle_stage_fftX(cplx *buf1, cplx *buf2, i64 n0, i64 n1l, i64 n2, int dire
 {
     const i64 rows = n1l * n2;
     if (direction == ORACLE_FORWARD) {
+        enum { TB = 16 };
 #pragma omp parallel for schedule(static)
-        for (i64 r = 0; r < rows; r++)
-            for (i64 x = 0; x < n0; x++) buf2[r * n0 + x] = buf1[x * rows + r];
+        for (i64 rb = 0; rb < rows; rb += TB)
+            for (i64 xb = 0; xb < n0; xb += TB)
+                for (i64 r = rb; r < rb + TB && r < rows; r++)
+                    for (i64 x = xb; x < xb + TB && x < n0; x++) buf2[r * n0 + x] = buf1[x * rows + r];
         oracle_fft_batch(buf2, (int)n0, 1, rows, rows, n0, 0, -1);
     } else {
         oracle_fft_batch(buf1, (int)n0, 1, rows, rows, n0, 0, +1);
+        enum { TB = 16 };
 #pragma omp parallel for schedule(static)
-        for (i64 x = 0; x < n0; x++)
-            for (i64 r = 0; r < rows; r++) buf2[x * rows + r] = buf1[r * n0 + x];
+        for (i64 xb = 0; xb < n0; xb += TB)
+            for (i64 rb = 0; rb < rows; rb += TB)
+                for (i64 x = xb; x < xb + TB && x < n0; x++)
+                    for (i64 r = rb; r < rb + TB && r < rows; r++) buf2[x * rows + r] = buf1[r * n0 + x];
     }
 }
 

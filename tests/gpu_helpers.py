@@ -12,7 +12,7 @@ from oracle import SlabGeometry
 CDT = {dfft.DOUBLE: (np.complex128, torch.complex128), dfft.FLOAT: (np.complex64, torch.complex64)}
 
 
-def run_slab(n0, n1, n2, P, direction, inputs, precision=dfft.DOUBLE, flags=0, repeat=1, stages=None, inplace=False):
+def run_slab(n0, n1, n2, P, direction, inputs, precision=dfft.DOUBLE, flags=0, repeat=1, stages=None, inplace=False, refill=True):
     """inputs[p]: numpy array (max_count) for device p's bufferDev1.  Returns dict with per-device
     'buf1', 'buf2' numpy copies after execution (and after each stage when `stages`)."""
     g = SlabGeometry(n0, n1, n2, P)
@@ -46,7 +46,7 @@ def run_slab(n0, n1, n2, P, direction, inputs, precision=dfft.DOUBLE, flags=0, r
                     out["stages"].append((fetch(plan.bufferDev1, mc), fetch(plan.bufferDev2, mc)))
             else:
                 for _ in range(repeat):
-                    if _ > 0:  # refill bufferDev1 like the reference driver (fftSpeed3d_c2c.cpp:78)
+                    if _ > 0 and refill:  # refill bufferDev1 like the reference driver (fftSpeed3d_c2c.cpp:78)
                         plan.synchronize()
                         torch.cuda.synchronize(dev)
                         h = np.zeros(mc, dtype=npdt); h[: inputs[p].size] = inputs[p]
