@@ -29,7 +29,7 @@ __all__ = [
     "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
-    "fft_lines", "memcpy_htod", "memcpy_dtoh",
+    "fft_lines", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
 ]
 
 
@@ -66,6 +66,8 @@ def lib():
     L.dfft_comm_create_local.argtypes = [i, P(vp)]
     L.dfft_comm_create_bootstrap.argtypes = [i, i, _ALLGATHER, vp, P(vp)]
     L.dfft_comm_destroy.argtypes = [vp]
+    L.dfft_comm_allgather.argtypes = [vp, i, vp, vp, ctypes.c_size_t]
+    L.dfft_exchange_table.argtypes = [ll, ll, ll, i, i, i, P(ll), P(ll), P(ll), P(ll)]
     L.dfft_plan_c2c_3d.argtypes = [ll, ll, ll, vp, vp, vp, i, i, i, i, u, P(vp)]
     for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange"):
         getattr(L, name).argtypes = [vp]
@@ -124,6 +126,21 @@ def fft_mpi_alloc_local_memory(count, flag, precision=DOUBLE):
     if not p:
         raise DfftError("fft_mpi_alloc_local_memory: " + lib().dfft_last_error().decode())
     return p
+
+
+def exchange_table(n0, n1, n2, totalDevCount, devIdx, direction):
+    """TransInfo of one device (fft_mpi_3d_api.cpp:84-133): dict of scount/soffset/rcount/roffset lists."""
+    arrs = [(ctypes.c_longlong * totalDevCount)() for _ in range(4)]
+    _check(lib().dfft_exchange_table(n0, n1, n2, totalDevCount, devIdx, direction, *arrs), "dfft_exchange_table")
+    return dict(zip(("scount", "soffset", "rcount", "roffset"), (list(x) for x in arrs)))
+
+
+def comm_allgather(comm, rank, payload: bytes):
+    """All-gather `payload` through a dfft communicator (the plan-creation bootstrap path)."""
+    n = comm.nranks
+    buf = ctypes.create_string_buffer(len(payload) * n)
+    _check(lib().dfft_comm_allgather(comm.handle, rank, payload, buf, len(payload)), "dfft_comm_allgather")
+    return [buf.raw[i * len(payload):(i + 1) * len(payload)] for i in range(n)]
 
 
 def fft_mpi_cleanup():

@@ -234,6 +234,14 @@ extern "C" int dfft_comm_create_bootstrap(int rank, int nranks, dfft_allgather_f
     return 0;
 }
 
+/* host-side all-gather through the communicator (what plan creation uses to exchange IPC handles) */
+extern "C" int dfft_comm_allgather(dfft_comm c, int rank, const void* send, void* recv, size_t bytes)
+{
+    if (!c || !send || !recv || rank < 0 || rank >= c->nranks) return fail(DFFT_EINVAL, "dfft_comm_allgather: bad arguments");
+    if (c->allgather(rank, send, recv, bytes) != 0) return fail(DFFT_ECOMM, "bootstrap allgather failed");
+    return 0;
+}
+
 extern "C" int dfft_comm_destroy(dfft_comm c)
 {
     delete c;
@@ -612,6 +620,22 @@ static long long recv_off(const Geom& g, int s, int r, int dir)
 static long long xchg_count(const Geom& g, int s, int r, int dir)
 {
     return dir == DFFT_FORWARD ? g.n0l(s) * g.n1l(r) * g.n2 : g.n0l(r) * g.n1l(s) * g.n2;
+}
+
+/* the reference's TransInfo table (fft_mpi_common.h:24-29, filled at api.cpp:84-133) */
+extern "C" int dfft_exchange_table(long long n0, long long n1, long long n2, int P, int dev, int direction, long long* scount,
+                                   long long* soffset, long long* rcount, long long* roffset)
+{
+    if (P < 1 || dev < 0 || dev >= P || (direction != DFFT_FORWARD && direction != DFFT_BACKWARD)) return fail(DFFT_EINVAL, "bad arguments");
+    Geom g{n0, n1, n2, P};
+    if (g.last_n0() < 1 || g.last_n1() < 1) return fail(DFFT_EUNSUPPORTED, "empty last slab");
+    for (int i = 0; i < P; i++) {
+        if (scount) scount[i] = xchg_count(g, dev, i, direction);
+        if (soffset) soffset[i] = send_off(g, dev, i, direction);
+        if (rcount) rcount[i] = xchg_count(g, i, dev, direction);
+        if (roffset) roffset[i] = recv_off(g, i, dev, direction);
+    }
+    return 0;
 }
 
 static int flags_signal(dfft_plan p, bool arrive, unsigned long long value)

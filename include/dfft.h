@@ -91,6 +91,12 @@ int dfft_comm_create_local(int nranks, dfft_comm* comm);
 /* One process per GPU; `allgather` is used during plan creation / teardown only. */
 int dfft_comm_create_bootstrap(int rank, int nranks, dfft_allgather_fn allgather, void* ctx, dfft_comm* comm);
 int dfft_comm_destroy(dfft_comm comm);
+/* host-side all-gather through a communicator (what plan creation uses to swap IPC handles / the NCCL id) */
+int dfft_comm_allgather(dfft_comm comm, int rank, const void* send, void* recv, size_t bytes);
+/* the reference's TransInfo exchange table of one device (fft_mpi_common.h:24-29, fft_mpi_3d_api.cpp:84-133):
+ * element counts and offsets of the chunk sent to / received from every device i */
+int dfft_exchange_table(long long n0, long long n1, long long n2, int total_devices, int dev_idx, int direction,
+                        long long* scount, long long* soffset, long long* rcount, long long* roffset);
 
 /* -- plan / execute ------------------------------------------------------------------------ */
 /* fft_mpi_plan_dft_c2c_3d, fft_mpi_3d_api.cpp:41-141.  Same ownership rules: `in`/`out` are the

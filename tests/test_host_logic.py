@@ -1,0 +1,133 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/dfft.h
+declares, slab bookkeeping matches the oracle's restatement of the reference, and the process-per-GPU
+bootstrap path works over a world_size-2 gloo group (no compute calls: there is no GPU here)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import distributedfft_b200 as dfft
+from oracle import BACKWARD, FORWARD, COracle, SlabGeometry, proper_device_num
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dfft.h")).read()
+    names = set(re.findall(r"\b(dfft_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"dfft_allgather_fn"}
+    assert len(names) >= 25
+    L = dfft.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_supported_lengths_cover_baseline_configs():
+    for prec in (dfft.DOUBLE, dfft.FLOAT):
+        ls = dfft.supported_lengths(prec)
+        for n in (64, 512, 768, 1024):
+            assert n in ls
+        assert ls == sorted(ls)
+
+
+def test_slab_bookkeeping_matches_oracle():
+    co = COracle()
+    for (n0, n1, n2, P) in [(512, 512, 512, 8), (10, 9, 4, 3), (9, 10, 4, 3), (64, 64, 64, 4), (768, 768, 768, 8), (7, 12, 4, 3)]:
+        g = SlabGeometry(n0, n1, n2, P)
+        for d in range(P):
+            assert dfft.getMaxDataCount(n0, n1, n2, P, d == P - 1) == co.lib.oracle_max_data_count(n0, n1, n2, P, int(d == P - 1))
+            alloc, ln0, s0, ln1, s1 = dfft.fft_mpi_local_size_3d(n0, n1, n2, P, d)
+            assert (alloc, ln0, s0, ln1, s1) == (g.max_count(d), g.n0l(d), d * g.xd, g.n1l(d), d * g.yd)
+            for direction in (FORWARD, BACKWARD):
+                mine = dfft.exchange_table(n0, n1, n2, P, d, direction)
+                ref = co.exchange_table(n0, n1, n2, P, d, direction)
+                for k in ("scount", "soffset", "rcount", "roffset"):
+                    assert mine[k] == list(ref[k]), (k, d, direction)
+
+
+def test_fft_mpi_init_device_policy():
+    """getProperDeviceNum (api.cpp:232-272): without a GPU the wanted count is not clamped."""
+    for n0, w in ((512, 8), (10, 4), (9, 4), (5, 4), (7, 3)):
+        tot, loc, counts = dfft.fft_mpi_init([n0, 64, 4], w)
+        assert tot == loc == proper_device_num(n0, w)
+        g = SlabGeometry(n0, 64, 4, tot)
+        assert counts == [g.in_count(p) for p in range(tot)]
+    with pytest.raises(dfft.DfftError):
+        dfft.fft_mpi_init([8, 3, 4], 4)   # N1=3 over 4 devices leaves an empty y-slab
+
+
+def test_plan_rejects_bad_arguments_without_touching_a_gpu():
+    with pytest.raises(dfft.DfftError, match="unsupported transform length"):
+        dfft.fft_mpi_plan_dft_c2c_3d(11, 16, 16, 1, 2, None, 0, 1, FORWARD)
+    with pytest.raises(dfft.DfftError, match="communicator"):
+        dfft.fft_mpi_plan_dft_c2c_3d(16, 16, 16, 1, 2, None, 0, 2, FORWARD)
+    with pytest.raises(dfft.DfftError, match="empty last slab"):
+        c = dfft.LocalComm(4)
+        try:
+            dfft.fft_mpi_plan_dft_c2c_3d(6, 16, 16, 1, 2, c, 0, 4, FORWARD)
+        finally:
+            c.destroy()
+
+
+def test_local_comm_allgather_threads():
+    import threading
+    P = 4
+    comm = dfft.LocalComm(P)
+    out = [None] * P
+
+    def w(r):
+        out[r] = dfft.comm_allgather(comm, r, bytes([r]) * 64)
+
+    th = [threading.Thread(target=w, args=(r,)) for r in range(P)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for r in range(P):
+        assert out[r] == [bytes([q]) * 64 for q in range(P)]
+    comm.destroy()
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+import distributedfft_b200 as dfft
+from oracle import SlabGeometry
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+def ag(b):
+    out = [None] * world
+    dist.all_gather_object(out, b)
+    return out
+comm = dfft.BootstrapComm(rank, world, ag)
+# 1. the bootstrap all-gather used for IPC handles / NCCL id (64- and 128-byte payloads)
+for size in (64, 128):
+    got = dfft.comm_allgather(comm, rank, bytes([rank + 1]) * size)
+    assert got == [bytes([q + 1]) * size for q in range(world)], got
+# 2. every rank's exchange table agrees with its peers' (scount[r] on me == rcount[me] on r)
+n0, n1, n2 = 10, 9, 4
+for direction in (1, -1):
+    mine = dfft.exchange_table(n0, n1, n2, world, rank, direction)
+    tabs = [None] * world
+    dist.all_gather_object(tabs, mine)
+    for r in range(world):
+        assert mine["scount"][r] == tabs[r]["rcount"][rank]
+        assert mine["rcount"][r] == tabs[r]["scount"][rank]
+    g = SlabGeometry(n0, n1, n2, world)
+    assert sum(mine["scount"]) == (g.in_count(rank) if direction == 1 else g.out_count(rank))
+comm.destroy()
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_bootstrap_comm_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
