@@ -463,6 +463,31 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         else if (env && !strcmp(env, "staged")) xmode = DFFT_EXCHANGE_STAGED;
         else xmode = DFFT_EXCHANGE_P2P;
     }
+    if (P > 1) {
+        // peer reachability (api.cpp:16-27 enables peer access in fft_mpi_init; done here so a plan does not
+        // depend on dfft_init having run).  Threads of one process map peers directly and need
+        // cudaDeviceEnablePeerAccess; separate processes get it from cudaIpcOpenMemHandle.
+        std::vector<int> devs(P);
+        if (comm->allgather(p->me, &p->device, devs.data(), sizeof(int)) != 0) return bail(fail(DFFT_ECOMM, "bootstrap allgather failed"));
+        int reach = 1;
+        if (comm->local) {
+            for (int q = 0; q < P; q++) {
+                if (q == p->me || devs[q] == p->device) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, p->device, devs[q]) != cudaSuccess || !can) { cudaGetLastError(); reach = 0; continue; }
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devs[q], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) reach = 0;
+                cudaGetLastError();
+            }
+        }
+        std::vector<int> all(P);
+        if (comm->allgather(p->me, &reach, all.data(), sizeof(int)) != 0) return bail(fail(DFFT_ECOMM, "bootstrap allgather failed"));
+        for (int q = 0; q < P; q++) reach &= all[q];
+        if (!reach) {
+            if ((flags & DFFT_EXCHANGE_MASK) == DFFT_EXCHANGE_AUTO && !getenv("DFFT_EXCHANGE")) xmode = DFFT_EXCHANGE_NCCL;
+            else if (xmode != DFFT_EXCHANGE_NCCL) return bail(fail(DFFT_ECOMM, "peer access between the devices is not available; use DFFT_EXCHANGE_NCCL"));
+        }
+    }
     p->xmode = xmode;
     if (xmode != DFFT_EXCHANGE_STAGED) CUP(cudaMalloc(&p->work, (size_t)p->max_count * p->esz));
     if (P > 1) {

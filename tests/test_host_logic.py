@@ -119,7 +119,7 @@ for direction in (1, -1):
 comm.destroy()
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\n" % rank); sys.stdout.flush()
 '''
 
 
