@@ -234,6 +234,10 @@ def run_dfft_arm(args):
     tout = torch.empty(maxc, dtype=tdt, device=dev)
     torch.cuda.synchronize(dev)
     flags = {"auto": dfft.EXCHANGE_AUTO, "p2p": dfft.EXCHANGE_P2P, "nccl": dfft.EXCHANGE_NCCL}[args.exchange]
+    if args.no_fuse:
+        flags |= dfft.NO_FUSE
+    if args.fuse:
+        flags |= dfft.FORCE_FUSE
     plan = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tin.data_ptr(), tout.data_ptr(), comm, rank, P, dfft.FORWARD, prec, flags)
     stream = torch.cuda.ExternalStream(plan.stream, device=dev)
 
@@ -286,12 +290,24 @@ def run_dfft_arm(args):
     value = F * 1e-9 / (ms_per_step * 1e-3)
     M = float(n) ** 3 / P
     peak, peak_src = measured_peak()
-    names = ["Z pass (contiguous, fft_tile_kernel MAP_T)", "Y pass (strided + fused pack, fft_tile_kernel MAP_C)",
-             "X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)"]
-    dom = max(range(3), key=lambda i: passes_avg[i])
-    alg_bytes = 2.0 * esz * M                       # one read + one write of the local slab per pass
-    achieved = alg_bytes / (passes_avg[dom] * 1e-3) * 1e-9
-    traffic = {512: 4.24e9}.get(n) if P == 1 and prec == dfft.DOUBLE else None   # ncu dram read+write per launch (profiles/)
+    slab_bytes = 2.0 * esz * M                      # one read + one write of the local slab (per axis pass)
+    if plan.fused:
+        # t0 is ONE kernel doing the Z and Y passes with the intermediate resident in L2: its compulsory HBM
+        # traffic is one read + one write of the slab (2*E*M); by SURVEY 8d's per-pass convention it does 4*E*M.
+        kernels = [("t0 fused Z+Y (fft_fused2_kernel: contiguous + strided role, intermediate L2-resident)", passes_avg[0], slab_bytes, 2 * slab_bytes, "t0_fused"),
+                   ("X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)", passes_avg[2], slab_bytes, slab_bytes, "x")]
+    else:
+        kernels = [("Z pass (contiguous, fft_tile_kernel MAP_T)", passes_avg[0], slab_bytes, slab_bytes, "z"),
+                   ("Y pass (strided + fused pack, fft_tile_kernel MAP_C)", passes_avg[1], slab_bytes, slab_bytes, "y"),
+                   ("X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)", passes_avg[2], slab_bytes, slab_bytes, "x")]
+    kname, kms, alg_bytes, conv_bytes, kkey = max(kernels, key=lambda k: k[1])
+    achieved = alg_bytes / (kms * 1e-3) * 1e-9
+    traffic = None
+    try:   # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, captured under profiles/ (see profiles/traffic.json)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{n}^3:{args.precision}:P{P}:{kkey}")
+    except Exception:
+        pass
     transform_bytes = (6.0 + (2.0 if (P > 1 and plan.exchange == dfft.EXCHANGE_NCCL) else 0.0)) * esz * M
     line = {
         "metric": "3D C2C forward FFT GFlops/s (5*N^3*log2(N^3)/t)", "value": value, "unit": "GFlops/s",
@@ -301,11 +317,13 @@ def run_dfft_arm(args):
         "config": {"workload": f"{n}x{n}x{n} C2C {args.precision} forward, slab decomposition over {P} GPU(s)",
                    "exchange": {1: "p2p-fused", 2: "nccl", 3: "staged"}[plan.exchange] if P > 1 else "none",
                    "l2": "inputs (%.2f GiB per GPU) exceed the 126 MB L2; no flush needed" % (M * esz / 2 ** 30),
-                   "parallelism": f"slab{P}"},
+                   "parallelism": f"slab{P}", "t0": "fused-L2" if plan.fused else "two-sweep"},
         "stage_ms": {"t0": stage[0], "t1": stage[1], "t2": stage[2], "t3": stage[3], "total": stage[4]},
-        "pass_ms": {"z": passes_avg[0], "y": passes_avg[1], "x": passes_avg[2]},
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "pass_ms": ({"t0_fused_zy": passes_avg[0], "x": passes_avg[2]} if plan.fused else
+                    {"z": passes_avg[0], "y": passes_avg[1], "x": passes_avg[2]}),
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                     "per_pass_convention_bytes_per_launch": conv_bytes, "kernel_ms": kms,
                      "peak_source": peak_src,
                      "transform": {"achieved": transform_bytes / (ms_per_step * 1e-3) * 1e-9,
                                    "frac": transform_bytes / (ms_per_step * 1e-3) * 1e-9 / peak,
@@ -343,6 +361,8 @@ def main():
     ap.add_argument("--precision", default="double", choices=["double", "float"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fuse", action="store_true", help="run t0 as two HBM sweeps (Z pass, Y pass) instead of the fused kernel")
+    ap.add_argument("--fuse", action="store_true", help="force the fused L2-resident t0 kernel (default: only with the P2P exchange)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

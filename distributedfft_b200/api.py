@@ -20,13 +20,15 @@ DOUBLE = 0
 FLOAT = 1
 EXCHANGE_AUTO, EXCHANGE_P2P, EXCHANGE_NCCL, EXCHANGE_STAGED = 0, 1, 2, 3
 SCALE_BACKWARD = 4
+NO_FUSE = 8
+FORCE_FUSE = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfft.so")
 
 __all__ = [
     "FORWARD", "BACKWARD", "ALLOC_CPU", "ALLOC_DEV", "DOUBLE", "FLOAT", "EXCHANGE_AUTO", "EXCHANGE_P2P",
-    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
+    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
     "fft_lines", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
@@ -69,7 +71,7 @@ def lib():
     L.dfft_comm_allgather.argtypes = [vp, i, vp, vp, ctypes.c_size_t]
     L.dfft_exchange_table.argtypes = [ll, ll, ll, i, i, i, P(ll), P(ll), P(ll), P(ll)]
     L.dfft_plan_c2c_3d.argtypes = [ll, ll, ll, vp, vp, vp, i, i, i, i, u, P(vp)]
-    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange"):
+    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused"):
         getattr(L, name).argtypes = [vp]
     L.dfft_execute_stage.argtypes = [vp, i]
     L.dfft_execute_host.argtypes = [vp, vp, vp]
@@ -231,6 +233,10 @@ class Plan:
     @property
     def exchange(self):
         return lib().dfft_plan_exchange(self.handle)
+
+    @property
+    def fused(self):
+        return bool(lib().dfft_plan_fused(self.handle))
 
     @property
     def stream(self):

@@ -363,6 +363,12 @@ struct dfft_plan_s {
     void* nccl = nullptr;
     int launches = 0;
     bool timed = false;
+    // fused two-pass t0 (L2-resident intermediate): per-plane completion counters + ticket words
+    bool fuse = false;
+    int lag = 0;
+    unsigned long long* plane_done = nullptr;
+    unsigned int* ticket = nullptr;
+    unsigned long long fuse_epoch = 0;
 };
 
 template <typename T> static void upload_lut(void** dst, int nstages, const int* rad)
@@ -453,6 +459,26 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         upload_lut<float>(&p->lut_x, ex->s_nstages, ex->s_rad);
     }
     CUP(cudaGetLastError());
+    // the fused kernels pair the contiguous and the strided role of one table entry: square planes only
+    {
+        // policy: the fused kernel wins when the strided role's stores are NVLink-bound (P2P exchange: the
+        // contiguous role then hides entirely under the link time); on one GPU / NCCL the two HBM-bound sweeps
+        // are currently faster (profiles/: SM-side time of both roles adds up), so it is opt-in there.
+        const char* env = getenv("DFFT_FUSE");
+        const bool can = n1 == n2 && ez->fused[FK_ZY] != nullptr;
+        bool want = P > 1 && (flags & DFFT_EXCHANGE_MASK) != DFFT_EXCHANGE_NCCL && (flags & DFFT_EXCHANGE_MASK) != DFFT_EXCHANGE_STAGED;
+        if (env) want = strcmp(env, "0") != 0;
+        if (flags & DFFT_FORCE_FUSE) want = true;
+        if (flags & DFFT_NO_FUSE) want = false;
+        p->fuse = can && want;
+        if (getenv("DFFT_LAG")) p->lag = atoi(getenv("DFFT_LAG"));
+        if (p->fuse) {
+            CUP(cudaMalloc((void**)&p->plane_done, (size_t)p->n0l * sizeof(unsigned long long)));
+            CUP(cudaMemset(p->plane_done, 0, (size_t)p->n0l * sizeof(unsigned long long)));
+            CUP(cudaMalloc((void**)&p->ticket, 2 * sizeof(unsigned int)));
+            CUP(cudaMemset(p->ticket, 0, 2 * sizeof(unsigned int)));
+        }
+    }
 
     // exchange mode
     int xmode = (int)(flags & DFFT_EXCHANGE_MASK);
@@ -537,6 +563,8 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->buf1) cudaFree(p->buf1);
     if (p->work) cudaFree(p->work);
     if (p->sync) cudaFree(p->sync);
+    if (p->plane_done) cudaFree(p->plane_done);
+    if (p->ticket) cudaFree(p->ticket);
     if (p->lut_z) cudaFree(p->lut_z);
     if (p->lut_y) cudaFree(p->lut_y);
     if (p->lut_x) cudaFree(p->lut_x);
@@ -600,6 +628,45 @@ template <typename T> struct Pass {
             for (int q = 0; q < p->P; q++) { ct.cptr[q] = chunk_base[q]; ct.SAq[q] = g.n1l(q) * g.n2; }
         }
         return launch(p, p->ey, mode == 0 ? PK_Y : (mode == 1 ? PK_Y_CO : PK_Y_CI), a);
+    }
+    // t0 in one persistent kernel (square planes): forward Z (zsrc -> mid) then Y (mid -> ydst, or chunked);
+    // backward Y (ysrc or chunked -> mid) then Z (mid -> mid).  ymode as in y_pass.
+    static int zy_fused(dfft_plan p, const void* src, void* mid, void* dst, int ymode, void* const* chunk_base, bool scale)
+    {
+        const Geom& g = p->g;
+        const SizeEntry* e = p->ez;
+        const bool fwd = p->direction == DFFT_FORWARD;
+        TileArgs<T> z{}, y{};
+        const int CZ = e->f_zC, CY = e->s_C;
+        z.lut = (const cx<T>*)p->lut_z; y.lut = (const cx<T>*)p->lut_y;
+        z.inv = y.inv = fwd ? 0 : 1;
+        // contiguous role, tiled per plane: tile (plane, b) = CZ lines starting at line b*CZ of the plane
+        z.G = (int)cdiv(g.n1, CZ); z.W = (int)g.n1; z.ntiles = p->n0l * z.G;
+        z.ia = Affine{g.n1 * g.n2, (long long)CZ * g.n2, g.n2, 1}; z.oa = z.ia;
+        z.do_scale = scale ? 1 : 0; z.scale = (T)(1.0 / ((double)g.n0 * (double)g.n1 * (double)g.n2));
+        y.G = (int)cdiv(g.n2, CY); y.W = (int)g.n2; y.ntiles = p->n0l * y.G;
+        y.ia = Affine{g.n1 * g.n2, CY, 1, g.n2}; y.oa = y.ia;
+        if (ymode != 0) {
+            ChunkTab& ct = ymode == 1 ? y.co : y.ci;
+            ct.ediv = (int)g.yd(); ct.nchunks = p->P;
+            for (int q = 0; q < p->P; q++) { ct.cptr[q] = chunk_base[q]; ct.SAq[q] = g.n1l(q) * g.n2; }
+        }
+        if (fwd) { z.in = (const cx<T>*)src; z.out = (cx<T>*)mid; y.in = (const cx<T>*)mid; y.out = (cx<T>*)dst; }
+        else { y.in = (const cx<T>*)src; y.out = (cx<T>*)mid; z.in = (const cx<T>*)mid; z.out = (cx<T>*)mid; }
+        FusedCtl c{};
+        c.plane_done = p->plane_done; c.ticket = p->ticket; c.planes = p->n0l;
+        c.GA = fwd ? z.G : y.G; c.GB = fwd ? y.G : z.G;
+        c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
+        c.lag = p->lag;
+        const int kind = fwd ? (ymode == 1 ? FK_ZY_CO : FK_ZY) : (ymode == 2 ? FK_YZ_CI : FK_YZ);
+        cudaEventRecord(p->pev[0][0], p->stream);
+        cudaError_t err = fwd ? e->fused[kind](&z, &y, &c, p->sms, p->stream) : e->fused[kind](&y, &z, &c, p->sms, p->stream);
+        cudaEventRecord(p->pev[0][1], p->stream);
+        cudaEventRecord(p->pev[1][0], p->stream);
+        cudaEventRecord(p->pev[1][1], p->stream);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "fused t0 launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
     }
     // forward X: src = [x][y_l][z] -> dst = [y_l][z][x]
     static int x_fwd(dfft_plan p, const void* src, void* dst)
@@ -714,18 +781,27 @@ template <typename T> static int execute_fused(dfft_plan p)
         // t0 (+t1): Z pass out of place (bufferDev1 survives), Y pass with the pack (and, P2P, the
         // all-to-all) folded into its store
         if (P == 1) {
-            if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
-            if ((rc = Pass<T>::y_pass(p, p->work, p->work, 0, nullptr))) return rc;
+            if (p->fuse) {
+                if ((rc = Pass<T>::zy_fused(p, p->buf1, p->work, p->work, 0, nullptr, false))) return rc;
+            } else {
+                if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
+                if ((rc = Pass<T>::y_pass(p, p->work, p->work, 0, nullptr))) return rc;
+            }
             CU(cudaEventRecord(p->ev[1], p->stream));
             CU(cudaEventRecord(p->ev[2], p->stream));
             if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
-            if ((rc = Pass<T>::z_pass(p, p->buf1, p->buf2, false))) return rc;
-            p->epoch++;
-            if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
-            if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base))) return rc;
+            p->epoch++;
+            if (p->fuse) {
+                if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
+                if ((rc = Pass<T>::zy_fused(p, p->buf1, p->buf2, nullptr, 1, base, false))) return rc;
+            } else {
+                if ((rc = Pass<T>::z_pass(p, p->buf1, p->buf2, false))) return rc;
+                if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;
+                if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base))) return rc;
+            }
             if ((rc = flags_signal(p, true, p->epoch))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
             if ((rc = flags_wait(p, true, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
@@ -733,10 +809,14 @@ template <typename T> static int execute_fused(dfft_plan p)
             if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
             if ((rc = flags_signal(p, false, p->epoch))) return rc;
         } else {
-            if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->buf2, send_off(g, me, q, DFFT_FORWARD), p->esz);
-            if ((rc = Pass<T>::y_pass(p, p->work, nullptr, 1, base))) return rc;
+            if (p->fuse) {
+                if ((rc = Pass<T>::zy_fused(p, p->buf1, p->work, nullptr, 1, base, false))) return rc;
+            } else {
+                if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
+                if ((rc = Pass<T>::y_pass(p, p->work, nullptr, 1, base))) return rc;
+            }
             CU(cudaEventRecord(p->ev[1], p->stream));
             if ((rc = nccl_exchange(p, p->buf2, p->work))) return rc;
             CU(cudaEventRecord(p->ev[2], p->stream));
@@ -749,7 +829,8 @@ template <typename T> static int execute_fused(dfft_plan p)
             if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
             CU(cudaEventRecord(p->ev[2], p->stream));
-            if ((rc = Pass<T>::y_pass(p, p->buf2, p->buf2, 0, nullptr))) return rc;
+            if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, p->buf2, p->buf2, nullptr, 0, nullptr, scale))) return rc; }
+            else if ((rc = Pass<T>::y_pass(p, p->buf2, p->buf2, 0, nullptr))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
             p->epoch++;
             if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;
@@ -762,7 +843,8 @@ template <typename T> static int execute_fused(dfft_plan p)
             CU(cudaEventRecord(p->ev[2], p->stream));
             void* cb[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
-            if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
+            if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale))) return rc; }
+            else if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
             if ((rc = flags_signal(p, false, p->epoch))) return rc;
         } else {
             if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
@@ -771,9 +853,10 @@ template <typename T> static int execute_fused(dfft_plan p)
             CU(cudaEventRecord(p->ev[2], p->stream));
             void* cb[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
-            if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
+            if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale))) return rc; }
+            else if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
         }
-        if ((rc = Pass<T>::z_pass(p, p->buf2, p->buf2, scale))) return rc;
+        if (!p->fuse && (rc = Pass<T>::z_pass(p, p->buf2, p->buf2, scale))) return rc;
         CU(cudaEventRecord(p->ev[3], p->stream));
     }
     p->timed = true;
@@ -925,6 +1008,7 @@ extern "C" int dfft_plan_counts(dfft_plan p, long long* ic, long long* oc, long 
 }
 extern "C" int dfft_plan_launches(dfft_plan p) { return p ? p->launches : 0; }
 extern "C" int dfft_plan_exchange(dfft_plan p) { return p ? p->xmode : 0; }
+extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? 1 : 0; }
 extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }
 
 // ------------------------------------------------------------------------------------------------

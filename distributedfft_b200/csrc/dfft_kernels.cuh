@@ -22,6 +22,16 @@ enum PassKind {
 
 typedef cudaError_t (*PassLaunchFn)(const void* tile_args, int sm_count, cudaStream_t stream);
 
+// two dependent passes over the same planes in one persistent kernel (fft_fused2_kernel)
+enum FusedKind {
+    FK_ZY = 0,     // forward t0: Z then Y, natural store
+    FK_ZY_CO,      // forward t0 + t1 (+ t2 over NVLink): Z then Y with the chunked (pack / peer) store
+    FK_YZ,         // backward t0: Y then Z
+    FK_YZ_CI,      // backward t1 + t0: Y with the chunked (unpack) load, then Z
+    FK_COUNT
+};
+typedef cudaError_t (*FusedLaunchFn)(const void* args_a, const void* args_b, const FusedCtl* ctl, int sm_count, cudaStream_t stream);
+
 struct SizeEntry {
     int N;
     int prec;             // 0 = double, 1 = float
@@ -29,6 +39,8 @@ struct SizeEntry {
     int z_nstages, z_rad[8];
     int s_nstages, s_rad[8];
     PassLaunchFn launch[PK_COUNT];
+    int f_zC;             // lines per contiguous tile inside the fused kernels (same CTA size as the strided role)
+    FusedLaunchFn fused[FK_COUNT];   // valid for square planes (N1 == N2 == N): both roles come from this entry
 };
 
 const SizeEntry* find_size_entry(int N, int prec);

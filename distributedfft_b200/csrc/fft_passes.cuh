@@ -97,53 +97,74 @@ template <int MAP, int C, int TT> __device__ __forceinline__ void thread_map(int
 template <typename C_> __device__ __forceinline__ C_ ld_stream(const C_* p) { return __ldcg(p); }
 template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { __stcg(p, v); }
 
-template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, int MINB,
-          bool PINGPONG>
-__global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<T> A)
-{
-    static_assert(S::valid(), "bad schedule");
-    static_assert(S::NSTAGES > 1 || MAPIN == MAPOUT, "a thread-map change needs an exchange");
+// ------------------------------------------------------------------------------------------
+// TileOp: everything one pass does to one tile, as a reusable device-side unit.  `setup` stages the
+// twiddle tile (TMA) and the chunk tables into the CTA's shared memory once; `run` loads a tile,
+// runs the Stockham stages and stores it.  fft_tile_kernel wraps one TileOp; fft_fused2_kernel
+// wraps two (Z then Y, or Y then Z) whose intermediate stays in L2.
+// Shared-memory carve-up of one TileOp (offsets from its base):
+//   [0, exch_bytes) exchange buffer | lut_bytes twiddles | 16 B mbarrier | tab_bytes chunk tables
+// ------------------------------------------------------------------------------------------
+template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG>
+struct TileOp {
     using SM = TileSmem<S, T, C, PINGPONG>;
-    constexpr int R = S::R, TT = S::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* exch = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* lut_s = reinterpret_cast<cx<T>*>(smem_raw + SM::exch_bytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM::exch_bytes + SM::lut_bytes);
-    unsigned char* tabs = smem_raw + SM::exch_bytes + SM::lut_bytes + 16;
-    int2* etab_i = reinterpret_cast<int2*>(tabs);
-    int2* etab_o = etab_i + S::N;
-    char** cptr_i = reinterpret_cast<char**>(etab_o + S::N);
-    char** cptr_o = cptr_i + DFFT_MAX_CHUNKS;
-    long long* saq_i = reinterpret_cast<long long*>(cptr_o + DFFT_MAX_CHUNKS);
-    long long* saq_o = saq_i + DFFT_MAX_CHUNKS;
+    static constexpr int R = S::R, TT = S::T, NT = S::T * C;
+    static constexpr bool CHUNKED = CHUNK_IN || CHUNK_OUT;
+    static constexpr size_t aux_bytes = SM::lut_bytes + 16 + (CHUNKED ? SM::tab_bytes : 0);   // everything but the exchange buffer
+    static constexpr int NTW = TWREG ? (S::tw_regs_total() > 0 ? S::tw_regs_total() : 1) : 1;
 
-    const int tid = threadIdx.x;
-    int t_in, c_in, t_out, c_out;
-    thread_map<MAPIN, C, TT>(tid, t_in, c_in);
-    thread_map<MAPOUT, C, TT>(tid, t_out, c_out);
+    struct Ctx {
+        cx<T>* exch;
+        cx<T>* lut_s;
+        int2 *etab_i, *etab_o;
+        char **cptr_i, **cptr_o;
+        long long *saq_i, *saq_o;
+        int t_in, c_in, t_out, c_out;
+        int pp;
+    };
 
-    // twiddle tile: global -> shared by one TMA bulk copy
-    stage_twiddles_tma<T>(lut_s, A.lut, S::lut_size(), bar);
-    if constexpr (CHUNK_IN || CHUNK_OUT) {
-        for (int e = tid; e < S::N; e += TT * C) {
-            if (CHUNK_IN) { int q = e / A.ci.ediv; q = q < A.ci.nchunks ? q : A.ci.nchunks - 1; etab_i[e] = make_int2(q, e - q * A.ci.ediv); }
-            if (CHUNK_OUT) { int q = e / A.co.ediv; q = q < A.co.nchunks ? q : A.co.nchunks - 1; etab_o[e] = make_int2(q, e - q * A.co.ediv); }
+    // exch: exchange buffer (SM::exch_bytes, may be shared with another TileOp); aux: aux_bytes of this op's own
+    static __device__ __forceinline__ void setup(const TileArgs<T>& A, unsigned char* exch, unsigned char* aux, Ctx& k)
+    {
+        const int tid = threadIdx.x;
+        k.exch = reinterpret_cast<cx<T>*>(exch);
+        k.lut_s = reinterpret_cast<cx<T>*>(aux);
+        uint64_t* bar = reinterpret_cast<uint64_t*>(aux + SM::lut_bytes);
+        unsigned char* tabs = aux + SM::lut_bytes + 16;
+        k.etab_i = reinterpret_cast<int2*>(tabs);
+        k.etab_o = k.etab_i + S::N;
+        k.cptr_i = reinterpret_cast<char**>(k.etab_o + S::N);
+        k.cptr_o = k.cptr_i + DFFT_MAX_CHUNKS;
+        k.saq_i = reinterpret_cast<long long*>(k.cptr_o + DFFT_MAX_CHUNKS);
+        k.saq_o = k.saq_i + DFFT_MAX_CHUNKS;
+        k.pp = 0;
+        thread_map<MAPIN, C, TT>(tid, k.t_in, k.c_in);
+        thread_map<MAPOUT, C, TT>(tid, k.t_out, k.c_out);
+        // twiddle tile: global -> shared by one TMA bulk copy
+        stage_twiddles_tma<T>(k.lut_s, A.lut, S::lut_size(), bar);
+        if constexpr (CHUNKED) {
+            for (int e = tid; e < S::N; e += NT) {
+                if (CHUNK_IN) { int q = e / A.ci.ediv; q = q < A.ci.nchunks ? q : A.ci.nchunks - 1; k.etab_i[e] = make_int2(q, e - q * A.ci.ediv); }
+                if (CHUNK_OUT) { int q = e / A.co.ediv; q = q < A.co.nchunks ? q : A.co.nchunks - 1; k.etab_o[e] = make_int2(q, e - q * A.co.ediv); }
+            }
+            if (tid < DFFT_MAX_CHUNKS) {
+                if (CHUNK_IN) { k.cptr_i[tid] = (char*)A.ci.cptr[tid]; k.saq_i[tid] = A.ci.SAq[tid]; }
+                if (CHUNK_OUT) { k.cptr_o[tid] = (char*)A.co.cptr[tid]; k.saq_o[tid] = A.co.SAq[tid]; }
+            }
+            __syncthreads();
         }
-        if (tid < DFFT_MAX_CHUNKS) {
-            if (CHUNK_IN) { cptr_i[tid] = (char*)A.ci.cptr[tid]; saq_i[tid] = A.ci.SAq[tid]; }
-            if (CHUNK_OUT) { cptr_o[tid] = (char*)A.co.cptr[tid]; saq_o[tid] = A.co.SAq[tid]; }
-        }
-        __syncthreads();
     }
 
-    cx<T> twr[TWREG ? (S::tw_regs_total() > 0 ? S::tw_regs_total() : 1) : 1];
-    if constexpr (TWREG) TwLoader<S, 0, T>::run(twr, t_in, t_out, lut_s);
+    static __device__ __forceinline__ void load_twiddles(const Ctx& k, cx<T>* twr)
+    {
+        if constexpr (TWREG) TwLoader<S, 0, T>::run(twr, k.t_in, k.t_out, k.lut_s);
+    }
 
-    const bool inv = A.inv != 0;   // inverse transform = swap(re,im) -> forward -> swap(re,im)
-    const bool do_scale = A.do_scale != 0;
-
-    int pp = 0;
-    for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+    static __device__ __forceinline__ void run(const TileArgs<T>& A, Ctx& k, long long tile, const cx<T>* twr)
+    {
+        const bool inv = A.inv != 0;   // inverse transform = swap(re,im) -> forward -> swap(re,im)
+        const bool do_scale = A.do_scale != 0;
+        const int t_in = k.t_in, c_in = k.c_in, t_out = k.t_out, c_out = k.c_out;
         const long long a = tile / A.G;
         const int b = (int)(tile - a * A.G);
         cx<T> v[R];
@@ -157,8 +178,8 @@ __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<
                 const long long off = b * A.ia.SB + c_in * A.ia.cs;
 #pragma unroll
                 for (int u = 0; u < R; u++) {
-                    const int2 qe = etab_i[t_in + u * TT];
-                    const cx<T>* p = reinterpret_cast<const cx<T>*>(cptr_i[qe.x]) + a * saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
+                    const int2 qe = k.etab_i[t_in + u * TT];
+                    const cx<T>* p = reinterpret_cast<const cx<T>*>(k.cptr_i[qe.x]) + a * k.saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
                     v[u] = ok ? ld_stream(p) : mk<T>(0, 0);
                 }
             }
@@ -167,7 +188,7 @@ __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<
                 for (int u = 0; u < R; u++) v[u] = cswap(v[u]);
             }
         }
-        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, exch, pp, lut_s, twr);
+        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, k.exch, k.pp, k.lut_s, twr);
         {
             if (inv) {
 #pragma unroll
@@ -187,13 +208,113 @@ __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<
                     const long long off = b * A.oa.SB + c_out * A.oa.cs;
 #pragma unroll
                     for (int u = 0; u < R; u++) {
-                        const int2 qe = etab_o[t_out + u * TT];
-                        cx<T>* p = reinterpret_cast<cx<T>*>(cptr_o[qe.x]) + a * saq_o[qe.x] + off + (long long)qe.y * A.oa.es;
+                        const int2 qe = k.etab_o[t_out + u * TT];
+                        cx<T>* p = reinterpret_cast<cx<T>*>(k.cptr_o[qe.x]) + a * k.saq_o[qe.x] + off + (long long)qe.y * A.oa.es;
                         st_stream(p, v[u]);
                     }
                 }
             }
         }
+    }
+};
+
+template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, int MINB,
+          bool PINGPONG>
+__global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<T> A)
+{
+    static_assert(S::valid(), "bad schedule");
+    static_assert(S::NSTAGES > 1 || MAPIN == MAPOUT, "a thread-map change needs an exchange");
+    using Op = TileOp<S, T, C, MAPIN, MAPOUT, TWREG, CHUNK_IN, CHUNK_OUT, PINGPONG>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename Op::Ctx k;
+    Op::setup(A, smem_raw, smem_raw + Op::SM::exch_bytes, k);
+    cx<T> twr[Op::NTW];
+    Op::load_twiddles(k, twr);
+    for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) Op::run(A, k, tile, twr);
+}
+
+// ------------------------------------------------------------------------------------------
+// Two dependent passes over the same planes in ONE persistent kernel (t0 = Z then Y forward, Y then Z
+// backward): the reference runs them as two launches per plane (fft_mpi_3d_api.cpp:496-502), we ran
+// them as two full HBM sweeps; here a plane's intermediate is produced and consumed while it is still
+// resident in the 126 MB L2, so t0 costs one HBM read + one HBM write of the slab.
+//
+// Work is handed out by a global ticket counter in an order that interleaves "role A on plane
+// x + lag" with "role B on plane x".  A role-B tile waits on its plane's completion counter
+// (release/acquire at gpu scope); every lower ticket is held by a running CTA and role-A tiles never
+// wait, so the scheme cannot deadlock whatever the residency.  The counters are monotonic
+// (target = epoch * tiles-per-plane); the last CTA to leave re-arms the ticket counter.
+// ------------------------------------------------------------------------------------------
+struct FusedCtl {
+    unsigned long long* plane_done;   // [planes]
+    unsigned int* ticket;             // [0] next ticket, [1] CTAs that have left
+    unsigned long long target;        // plane_done value that means "role A finished this plane in this execute"
+    long long planes;
+    int GA, GB;                       // tiles per plane of role A / role B
+    int lag;                          // role A runs this many planes ahead of role B
+};
+
+template <class OpA, class OpB, typename T, int MINB>
+__global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArgs<T> A, const TileArgs<T> B, const FusedCtl F)
+{
+    static_assert(OpA::NT == OpB::NT, "both roles use the whole CTA");
+    constexpr size_t exch = OpA::SM::exch_bytes > OpB::SM::exch_bytes ? OpA::SM::exch_bytes : OpB::SM::exch_bytes;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_ticket;
+    typename OpA::Ctx ka;
+    typename OpB::Ctx kb;
+    OpA::setup(A, smem_raw, smem_raw + exch, ka);
+    OpB::setup(B, smem_raw, smem_raw + exch + OpA::aux_bytes, kb);
+    cx<T> twa[OpA::NTW], twb[OpB::NTW];
+    OpA::load_twiddles(ka, twa);
+    OpB::load_twiddles(kb, twb);
+
+    const long long lag = F.lag < F.planes ? F.lag : F.planes;
+    const long long headT = lag * F.GA;                          // role A on planes [0, lag)
+    const long long midT = (F.planes - lag) * (F.GA + F.GB);     // pairs: A on plane lag+i, then B on plane i
+    const long long total = headT + midT + lag * F.GB;           // tail: B on the last `lag` planes
+    for (;;) {
+        __syncthreads();   // previous tile's smem traffic and s_ticket readers are done
+        if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(F.ticket, 1u);
+        __syncthreads();
+        const long long t = s_ticket;
+        if (t >= total) break;
+        bool roleA;
+        long long plane, idx;
+        if (t < headT) { roleA = true; plane = t / F.GA; idx = t - plane * F.GA; }
+        else if (t < headT + midT) {
+            const long long u = t - headT, i = u / (F.GA + F.GB), r = u - i * (F.GA + F.GB);
+            if (r < F.GA) { roleA = true; plane = lag + i; idx = r; }
+            else { roleA = false; plane = i; idx = r - F.GA; }
+        } else {
+            const long long u = t - headT - midT, i = u / F.GB;
+            roleA = false; plane = F.planes - lag + i; idx = u - i * F.GB;
+        }
+        if (roleA) {
+            OpA::run(A, ka, plane * F.GA + idx, twa);
+            __syncthreads();                       // every thread's stores are issued ...
+            if (threadIdx.x == 0) {
+                __threadfence();                   // ... and ordered before the release
+                atomicAdd(F.plane_done + plane, 1ull);
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                unsigned long long v;
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(F.plane_done + plane) : "memory");
+                    if (v >= F.target) break;
+                    __nanosleep(64);
+                    if (++spins > (1u << 25)) __trap();   // a lost dependency traps instead of hanging the GPU
+                }
+            }
+            __syncthreads();
+            OpB::run(B, kb, plane * F.GB + idx, twb);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const unsigned left = atomicAdd(F.ticket + 1, 1u);
+        if (left == gridDim.x - 1) { F.ticket[0] = 0; F.ticket[1] = 0; __threadfence(); }
     }
 }
 

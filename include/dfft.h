@@ -47,6 +47,11 @@ extern "C" {
 #define DFFT_SCALE_BACKWARD 4u   /* divide by N0*N1*N2 in the last backward pass (the `roc` variant's scale_element,
                                     3dmpifft_roc/include/fft_mpi_3d_api.cpp:208-210); default off like 3dmpifft_opt */
 
+#define DFFT_NO_FUSE 8u          /* t0 as two HBM sweeps (Z pass, Y pass) */
+#define DFFT_FORCE_FUSE 16u      /* t0 as ONE persistent kernel whose Z->Y intermediate stays in L2 (square planes only).
+                                    Default: fused when the exchange is P2P (the Y stores are NVLink-bound and hide the
+                                    Z role), two sweeps otherwise */
+
 #define DFFT_EINVAL (-1)
 #define DFFT_ECUDA (-2)
 #define DFFT_EUNSUPPORTED (-3)
@@ -130,6 +135,8 @@ int dfft_plan_buffers(dfft_plan plan, void** buffer1, void** buffer2);
 int dfft_plan_counts(dfft_plan plan, long long* in_count, long long* out_count, long long* max_count);
 /* kernels launched by the last execute (for bench.py's gpu_launches) */
 int dfft_plan_launches(dfft_plan plan);
+/* 1 when t0 runs as the fused two-pass kernel (square planes, N1 == N2), else 0 */
+int dfft_plan_fused(dfft_plan plan);
 /* which exchange the plan resolved to (DFFT_EXCHANGE_*) */
 int dfft_plan_exchange(dfft_plan plan);
 /* the stream the plan launches on (a cudaStream_t), so callers can time with events on it */

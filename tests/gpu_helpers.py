@@ -56,6 +56,7 @@ def run_slab(n0, n1, n2, P, direction, inputs, precision=dfft.DOUBLE, flags=0, r
                 out["timings"] = plan.timings()
                 out["launches"] = plan.launches
                 out["exchange"] = plan.exchange
+                out["fused"] = plan.fused
             out["buf1"] = fetch(plan.bufferDev1, mc)
             out["buf2"] = fetch(plan.bufferDev2, mc)
             out["counts"] = (plan.in_count, plan.out_count, plan.maxDataCountInDevice)

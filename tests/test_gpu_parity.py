@@ -205,3 +205,22 @@ def test_baseline_512_cube_properties_and_roundtrip(co):
     assert drv_metric <= 1e-11, drv_metric
     plan.destroy(); planb.destroy()
     assert t[4] > 0
+
+
+@pytest.mark.parametrize("n,n0", [(64, 48), (512, 24), (96, 6), (256, 4), (10, 32), (1024, 6)])
+def test_fused_t0_is_bitwise_the_two_sweep_t0(n, n0):
+    """The fused persistent t0 kernel (Z and Y roles, intermediate in L2, per-plane completion counters)
+    runs the same butterflies in the same order as the two-sweep path: results must be bit-identical,
+    forward and backward, over several executes (the counters are monotonic across executes)."""
+    rng = np.random.default_rng(n + n0)
+    A = rng.standard_normal((n0, n, n)) + 1j * rng.standard_normal((n0, n, n))
+    for direction in (FORWARD, BACKWARD):
+        inp = A.reshape(-1) if direction == FORWARD else A.transpose(1, 2, 0).reshape(-1)
+        a = run_slab(n0, n, n, 1, direction, [inp], repeat=3, refill=False, flags=dfft.FORCE_FUSE)
+        b = run_slab(n0, n, n, 1, direction, [inp], repeat=3, refill=False, flags=dfft.NO_FUSE)
+        assert a[0]["fused"] and not b[0]["fused"]
+        assert a[0]["launches"] == 2 and b[0]["launches"] == 3
+        assert np.array_equal(a[0]["buf2"], b[0]["buf2"]), (n, n0, direction)
+    ref = np.fft.fftn(A).transpose(1, 2, 0).reshape(-1)
+    f = run_slab(n0, n, n, 1, FORWARD, [A.reshape(-1)], flags=dfft.FORCE_FUSE)
+    assert np.abs(f[0]["buf2"] - ref).max() <= 1e-12 * np.log2(A.size) * np.abs(ref).max()
