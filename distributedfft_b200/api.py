@@ -75,6 +75,7 @@ def lib():
         getattr(L, name).argtypes = [vp]
     L.dfft_execute_stage.argtypes = [vp, i]
     L.dfft_execute_host.argtypes = [vp, vp, vp]
+    L.dfft_execute_host_async.argtypes = [vp, vp, vp]
     L.dfft_get_timings.argtypes = [vp, P(ctypes.c_double)]
     L.dfft_get_pass_timings.argtypes = [vp, P(ctypes.c_double)]
     L.dfft_plan_buffers.argtypes = [vp, P(vp), P(vp)]
@@ -212,6 +213,9 @@ class Plan:
 
     def execute_host(self, host_in_ptr, host_out_ptr):
         _check(lib().dfft_execute_host(self.handle, host_in_ptr, host_out_ptr), "dfft_execute_host")
+
+    def execute_host_async(self, host_in_ptr, host_out_ptr):
+        _check(lib().dfft_execute_host_async(self.handle, host_in_ptr, host_out_ptr), "dfft_execute_host_async")
 
     def synchronize(self):
         _check(lib().dfft_synchronize(self.handle), "dfft_synchronize")

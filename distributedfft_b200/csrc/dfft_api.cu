@@ -452,11 +452,11 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     if (precision == DFFT_DOUBLE) {
         upload_lut<double>(&p->lut_z, ez->z_nstages, ez->z_rad);
         upload_lut<double>(&p->lut_y, ey->s_nstages, ey->s_rad);
-        upload_lut<double>(&p->lut_x, ex->s_nstages, ex->s_rad);
+        upload_lut<double>(&p->lut_x, ex->x_nstages, ex->x_rad);
     } else {
         upload_lut<float>(&p->lut_z, ez->z_nstages, ez->z_rad);
         upload_lut<float>(&p->lut_y, ey->s_nstages, ey->s_rad);
-        upload_lut<float>(&p->lut_x, ex->s_nstages, ex->s_rad);
+        upload_lut<float>(&p->lut_x, ex->x_nstages, ex->x_rad);
     }
     CUP(cudaGetLastError());
     // the fused kernels pair the contiguous and the strided role of one table entry: square planes only
@@ -618,7 +618,7 @@ template <typename T> struct Pass {
     {
         const Geom& g = p->g;
         TileArgs<T> a{};
-        const int C = p->ey->s_C;
+        const int C = mode == 1 ? p->ey->p_C : p->ey->s_C;
         a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_y;
         a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n0l * a.G;
         a.ia = Affine{g.n1 * g.n2, C, 1, g.n2}; a.oa = a.ia;
@@ -637,7 +637,7 @@ template <typename T> struct Pass {
         const SizeEntry* e = p->ez;
         const bool fwd = p->direction == DFFT_FORWARD;
         TileArgs<T> z{}, y{};
-        const int CZ = e->f_zC, CY = e->s_C;
+        const int CZ = (fwd && ymode == 1) ? e->f_zCp : e->f_zC, CY = (fwd && ymode == 1) ? e->p_C : e->s_C;
         z.lut = (const cx<T>*)p->lut_z; y.lut = (const cx<T>*)p->lut_y;
         z.inv = y.inv = fwd ? 0 : 1;
         // contiguous role, tiled per plane: tile (plane, b) = CZ lines starting at line b*CZ of the plane
@@ -673,7 +673,7 @@ template <typename T> struct Pass {
     {
         const Geom& g = p->g;
         TileArgs<T> a{};
-        const int C = p->ex->s_C;
+        const int C = p->ex->x_C;
         a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_x;
         a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n1l * a.G;
         a.ia = Affine{g.n2, C, 1, p->n1l * g.n2};
@@ -685,7 +685,7 @@ template <typename T> struct Pass {
     {
         const Geom& g = p->g;
         TileArgs<T> a{};
-        const int C = p->ex->s_C;
+        const int C = p->ex->x_C;
         a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_x;
         a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n1l * a.G;
         a.ia = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
@@ -979,7 +979,7 @@ extern "C" int dfft_get_pass_timings(dfft_plan p, double t[3])
     return 0;
 }
 
-extern "C" int dfft_execute_host(dfft_plan p, const void* host_in, void* host_out)
+extern "C" int dfft_execute_host_async(dfft_plan p, const void* host_in, void* host_out)
 {
     if (!p || !host_in || !host_out) return fail(DFFT_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
@@ -987,6 +987,13 @@ extern "C" int dfft_execute_host(dfft_plan p, const void* host_in, void* host_ou
     int rc = dfft_execute(p);
     if (rc) return rc;
     CU(cudaMemcpyAsync(host_out, p->buf2, (size_t)p->out_count * p->esz, cudaMemcpyDeviceToHost, p->stream));
+    return 0;
+}
+
+extern "C" int dfft_execute_host(dfft_plan p, const void* host_in, void* host_out)
+{
+    int rc = dfft_execute_host_async(p, host_in, host_out);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(p->stream));
     return 0;
 }

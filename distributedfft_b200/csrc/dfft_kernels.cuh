@@ -34,12 +34,14 @@ typedef cudaError_t (*FusedLaunchFn)(const void* args_a, const void* args_b, con
 
 struct SizeEntry {
     int N;
+    int variant;          // 0 = default; > 0 = alternate tuning of the same length, selected with DFFT_VARIANT (experiments)
     int prec;             // 0 = double, 1 = float
-    int z_C, s_C;         // lines per tile of the contiguous / strided kernels
-    int z_nstages, z_rad[8];
-    int s_nstages, s_rad[8];
+    int z_C, s_C, p_C, x_C;   // lines per tile: contiguous (Z), strided local (Y), strided with peer/packed store, X passes
+    int z_nstages, z_rad[12];
+    int s_nstages, s_rad[12];
+    int x_nstages, x_rad[12];
     PassLaunchFn launch[PK_COUNT];
-    int f_zC;             // lines per contiguous tile inside the fused kernels (same CTA size as the strided role)
+    int f_zC, f_zCp;      // lines per contiguous tile inside the fused kernels (same CTA size as the strided role; p: peer-store kind)
     FusedLaunchFn fused[FK_COUNT];   // valid for square planes (N1 == N2 == N): both roles come from this entry
 };
 

@@ -1,5 +1,6 @@
 // size table lookup, twiddle tables, and the element-wise helper kernels of the staged mode
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include "dfft_kernels.cuh"
 
@@ -18,16 +19,22 @@ static std::vector<SizeEntry>& table()
 
 const SizeEntry* find_size_entry(int N, int prec)
 {
-    for (const SizeEntry& e : table())
-        if (e.N == N && e.prec == prec) return &e;
-    return nullptr;
+    const char* env = getenv("DFFT_VARIANT");
+    const int want = env ? atoi(env) : 0;
+    const SizeEntry* def = nullptr;
+    for (const SizeEntry& e : table()) {
+        if (e.N != N || e.prec != prec) continue;
+        if (e.variant == want) return &e;
+        if (e.variant == 0) def = &e;
+    }
+    return def;
 }
 
 void list_sizes(int prec, std::vector<int>& out)
 {
     out.clear();
     for (const SizeEntry& e : table())
-        if (e.prec == prec) out.push_back(e.N);
+        if (e.prec == prec && e.variant == 0) out.push_back(e.N);
 }
 
 template <typename T> std::vector<cx<T>> build_lut(int nstages, const int* rad)

@@ -2,6 +2,7 @@
 // instantiation units.
 #pragma once
 #include <atomic>
+#include <type_traits>
 #include "dfft_kernels.cuh"
 
 namespace dfft {
@@ -69,37 +70,55 @@ template <class S> void fill_rad(int& n, int* rad)
     for (int i = 0; i < S::NSTAGES; i++) rad[i] = S::rad(i);
 }
 
-// ZS/SS: schedules; ZC/SC lines per tile; *TW twiddles in registers; *MB min CTAs/SM; *PP ping-pong smem
-template <typename T, class ZS, int ZC, bool ZTW, int ZMB, bool ZPP, class SS, int SC, bool STW, int SMB, bool SPP>
-SizeEntry make_entry()
+// One kernel configuration: schedule, lines per tile, twiddles in registers, min CTAs/SM, ping-pong exchange buffer
+template <class S_, int C_, bool TW_, int MB_, bool PP_> struct Cfg {
+    using S = S_;
+    static constexpr int C = C_, MB = MB_;
+    static constexpr bool TW = TW_, PP = PP_;
+};
+
+// Z: contiguous pass.  Y: strided pass on local memory (t0 axis-1, backward unpack).  X: the t3 passes (strided on one
+// side, contiguous on the other).  PEER: the Y pass with the chunked store (pack / peer receive buffers over NVLink),
+// which wants >= 128-byte row segments; must use Y's schedule (it shares the twiddle table).
+template <typename T, class Z, class Y, class X = Y, class PEER = Y>
+SizeEntry make_entry(int variant = 0)
 {
+    using ZS = typename Z::S;
+    using SS = typename Y::S;
+    using XS = typename X::S;
+    static_assert(std::is_same<typename PEER::S, SS>::value, "the peer-store configuration shares the Y schedule");
     SizeEntry e{};
     e.N = ZS::N;
+    e.variant = variant;
     e.prec = sizeof(T) == 8 ? 0 : 1;
-    e.z_C = ZC;
-    e.s_C = SC;
+    e.z_C = Z::C;
+    e.s_C = Y::C;
+    e.p_C = PEER::C;
+    e.x_C = X::C;
     fill_rad<ZS>(e.z_nstages, e.z_rad);
     fill_rad<SS>(e.s_nstages, e.s_rad);
-    e.launch[PK_Z] = launch_pass<ZS, T, ZC, MAP_T, MAP_T, ZTW, false, false, ZMB, ZPP>;
-    e.launch[PK_Y] = launch_pass<SS, T, SC, MAP_C, MAP_C, STW, false, false, SMB, SPP>;
-    e.launch[PK_Y_CO] = launch_pass<SS, T, SC, MAP_C, MAP_C, STW, false, true, SMB, SPP>;
-    e.launch[PK_Y_CI] = launch_pass<SS, T, SC, MAP_C, MAP_C, STW, true, false, SMB, SPP>;
-    e.launch[PK_XF] = launch_pass<SS, T, SC, MAP_C, MAP_T, STW, false, false, SMB, SPP>;
-    e.launch[PK_XB] = launch_pass<SS, T, SC, MAP_T, MAP_C, STW, false, false, SMB, SPP>;
-    e.launch[PK_XB_CO] = launch_pass<SS, T, SC, MAP_T, MAP_C, STW, false, true, SMB, SPP>;
+    fill_rad<XS>(e.x_nstages, e.x_rad);
+    e.launch[PK_Z] = launch_pass<ZS, T, Z::C, MAP_T, MAP_T, Z::TW, false, false, Z::MB, Z::PP>;
+    e.launch[PK_Y] = launch_pass<SS, T, Y::C, MAP_C, MAP_C, Y::TW, false, false, Y::MB, Y::PP>;
+    e.launch[PK_Y_CO] = launch_pass<SS, T, PEER::C, MAP_C, MAP_C, PEER::TW, false, true, PEER::MB, PEER::PP>;
+    e.launch[PK_Y_CI] = launch_pass<SS, T, Y::C, MAP_C, MAP_C, Y::TW, true, false, Y::MB, Y::PP>;
+    e.launch[PK_XF] = launch_pass<XS, T, X::C, MAP_C, MAP_T, X::TW, false, false, X::MB, X::PP>;
+    e.launch[PK_XB] = launch_pass<XS, T, X::C, MAP_T, MAP_C, X::TW, false, false, X::MB, X::PP>;
+    e.launch[PK_XB_CO] = launch_pass<XS, T, X::C, MAP_T, MAP_C, X::TW, false, true, X::MB, X::PP>;
     // fused two-pass kernels: the contiguous role is re-tiled so that both roles fill the same CTA
-    constexpr int NT = SS::T * SC;
-    static_assert(NT % ZS::T == 0, "strided CTA size must be a multiple of the contiguous line's thread count");
-    constexpr int FZC = NT / ZS::T;
-    e.f_zC = FZC;
-    using OZ = TileOp<ZS, T, FZC, MAP_T, MAP_T, false, false, false, false>;
-    using OY = TileOp<SS, T, SC, MAP_C, MAP_C, false, false, false, false>;
-    using OYco = TileOp<SS, T, SC, MAP_C, MAP_C, false, false, true, false>;
-    using OYci = TileOp<SS, T, SC, MAP_C, MAP_C, false, true, false, false>;
-    e.fused[FK_ZY] = launch_fused<OZ, OY, T, SMB>;
-    e.fused[FK_ZY_CO] = launch_fused<OZ, OYco, T, SMB>;
-    e.fused[FK_YZ] = launch_fused<OY, OZ, T, SMB>;
-    e.fused[FK_YZ_CI] = launch_fused<OYci, OZ, T, SMB>;
+    constexpr int NT = SS::T * Y::C, NTP = SS::T * PEER::C;
+    static_assert(NT % ZS::T == 0 && NTP % ZS::T == 0, "strided CTA size must be a multiple of the contiguous line's thread count");
+    e.f_zC = NT / ZS::T;
+    e.f_zCp = NTP / ZS::T;
+    using OZ = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false>;
+    using OZp = TileOp<ZS, T, NTP / ZS::T, MAP_T, MAP_T, false, false, false, false>;
+    using OY = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, false, false, false>;
+    using OYco = TileOp<SS, T, PEER::C, MAP_C, MAP_C, false, false, true, false>;
+    using OYci = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, true, false, false>;
+    e.fused[FK_ZY] = launch_fused<OZ, OY, T, Y::MB>;
+    e.fused[FK_ZY_CO] = launch_fused<OZp, OYco, T, PEER::MB>;
+    e.fused[FK_YZ] = launch_fused<OY, OZ, T, Y::MB>;
+    e.fused[FK_YZ_CI] = launch_fused<OYci, OZ, T, Y::MB>;
     return e;
 }
 

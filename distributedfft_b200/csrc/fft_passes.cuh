@@ -58,11 +58,14 @@ struct StageRunner {
     static constexpr int LAST = S::NSTAGES - 1;
     static constexpr int LS = SmemGeom<T>::line(S::N, C);
     // thread (t_in, c_in) for every stage but the last, (t_out, c_out) for the last one
+    // `hook` runs once, right after the first stage's butterflies have consumed the loaded registers
+    template <class Hook>
     static __device__ __forceinline__ void run(cx<T>* v, int t_in, int c_in, int t_out, int c_out, cx<T>* exch,
-                                               int& pp, const cx<T>* lut, const cx<T>* twr)
+                                               int& pp, const cx<T>* lut, const cx<T>* twr, Hook&& hook)
     {
         const int t = (s == LAST) ? t_out : t_in;
         stage_compute<S, s, T, TWREG>(v, t, lut, twr);
+        if constexpr (s == 0) hook();
         if constexpr (s < LAST) {
             cx<T>* buf = exch + (PINGPONG ? (size_t)pp * C * LS : 0);
             if constexpr (!PINGPONG) __syncthreads();   // previous readers of the single buffer are done
@@ -72,7 +75,7 @@ struct StageRunner {
             else stage_gather<S, T>(v, t_in, buf + c_in * LS);
             pp ^= 1;
             StageRunner<S, s + 1, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, exch, pp, lut,
-                                                                    twr + S::tw_regs(s));
+                                                                    twr + S::tw_regs(s), hook);
         }
     }
 };
@@ -97,6 +100,18 @@ template <int MAP, int C, int TT> __device__ __forceinline__ void thread_map(int
 template <typename C_> __device__ __forceinline__ C_ ld_stream(const C_* p) { return __ldcg(p); }
 template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { __stcg(p, v); }
 
+// per-thread asynchronous global -> shared copies (LDGSTS): the next tile's elements are fetched into the
+// thread's private staging slots while the current tile is being transformed
+template <int BYTES> __device__ __forceinline__ void cp_async(void* dst_smem, const void* src)
+{
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // TileOp: everything one pass does to one tile, as a reusable device-side unit.  `setup` stages the
 // twiddle tile (TMA) and the chunk tables into the CTA's shared memory once; `run` loads a tile,
@@ -105,12 +120,15 @@ template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { 
 // Shared-memory carve-up of one TileOp (offsets from its base):
 //   [0, exch_bytes) exchange buffer | lut_bytes twiddles | 16 B mbarrier | tab_bytes chunk tables
 // ------------------------------------------------------------------------------------------
-template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG>
+template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG, bool PF = false>
 struct TileOp {
     using SM = TileSmem<S, T, C, PINGPONG>;
     static constexpr int R = S::R, TT = S::T, NT = S::T * C;
     static constexpr bool CHUNKED = CHUNK_IN || CHUNK_OUT;
-    static constexpr size_t aux_bytes = SM::lut_bytes + 16 + (CHUNKED ? SM::tab_bytes : 0);   // everything but the exchange buffer
+    // PF: software prefetch.  Element u of thread tid of the NEXT tile is copied asynchronously into the private slot
+    // stage[u * NT + tid] (conflict-free, never touched by another thread, so no barrier is involved).
+    static constexpr size_t stage_bytes = PF ? (size_t)R * NT * sizeof(cx<T>) : 0;
+    static constexpr size_t aux_bytes = SM::lut_bytes + 16 + (CHUNKED ? SM::tab_bytes : 0) + stage_bytes;   // everything but the exchange buffer
     static constexpr int NTW = TWREG ? (S::tw_regs_total() > 0 ? S::tw_regs_total() : 1) : 1;
 
     struct Ctx {
@@ -121,6 +139,7 @@ struct TileOp {
         long long *saq_i, *saq_o;
         int t_in, c_in, t_out, c_out;
         int pp;
+        cx<T>* stage;
     };
 
     // exch: exchange buffer (SM::exch_bytes, may be shared with another TileOp); aux: aux_bytes of this op's own
@@ -138,6 +157,7 @@ struct TileOp {
         k.saq_i = reinterpret_cast<long long*>(k.cptr_o + DFFT_MAX_CHUNKS);
         k.saq_o = k.saq_i + DFFT_MAX_CHUNKS;
         k.pp = 0;
+        k.stage = reinterpret_cast<cx<T>*>(aux + SM::lut_bytes + 16 + (CHUNKED ? SM::tab_bytes : 0));
         thread_map<MAPIN, C, TT>(tid, k.t_in, k.c_in);
         thread_map<MAPOUT, C, TT>(tid, k.t_out, k.c_out);
         // twiddle tile: global -> shared by one TMA bulk copy
@@ -160,7 +180,38 @@ struct TileOp {
         if constexpr (TWREG) TwLoader<S, 0, T>::run(twr, k.t_in, k.t_out, k.lut_s);
     }
 
-    static __device__ __forceinline__ void run(const TileArgs<T>& A, Ctx& k, long long tile, const cx<T>* twr)
+    // issue the asynchronous loads of `tile` into this thread's staging slots (PF only)
+    static __device__ __forceinline__ void prefetch(const TileArgs<T>& A, const Ctx& k, long long tile)
+    {
+        if constexpr (PF) {
+            const int t_in = k.t_in, c_in = k.c_in;
+            const long long a = tile / A.G;
+            const int b = (int)(tile - a * A.G);
+            const bool ok = b * C + c_in < A.W;
+            cx<T>* slot = k.stage + threadIdx.x;
+            if constexpr (!CHUNK_IN) {
+                const cx<T>* p = A.in + a * A.ia.SA + b * A.ia.SB + c_in * A.ia.cs + (long long)t_in * A.ia.es;
+#pragma unroll
+                for (int u = 0; u < R; u++) {
+                    if (ok) cp_async<sizeof(cx<T>)>(slot + u * NT, p + (long long)u * TT * A.ia.es);
+                    else slot[u * NT] = mk<T>(0, 0);
+                }
+            } else {
+                const long long off = b * A.ia.SB + c_in * A.ia.cs;
+#pragma unroll
+                for (int u = 0; u < R; u++) {
+                    const int2 qe = k.etab_i[t_in + u * TT];
+                    const cx<T>* p = reinterpret_cast<const cx<T>*>(k.cptr_i[qe.x]) + a * k.saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
+                    if (ok) cp_async<sizeof(cx<T>)>(slot + u * NT, p);
+                    else slot[u * NT] = mk<T>(0, 0);
+                }
+            }
+            cp_async_commit();
+        }
+    }
+
+    // next_tile < 0: nothing to prefetch.  With PF the caller must have prefetched `tile` before the first call.
+    static __device__ __forceinline__ void run(const TileArgs<T>& A, Ctx& k, long long tile, const cx<T>* twr, long long next_tile = -1)
     {
         const bool inv = A.inv != 0;   // inverse transform = swap(re,im) -> forward -> swap(re,im)
         const bool do_scale = A.do_scale != 0;
@@ -168,7 +219,16 @@ struct TileOp {
         const long long a = tile / A.G;
         const int b = (int)(tile - a * A.G);
         cx<T> v[R];
-        {
+        if constexpr (PF) {
+            cp_async_wait_all();
+            const cx<T>* slot = k.stage + threadIdx.x;
+#pragma unroll
+            for (int u = 0; u < R; u++) v[u] = slot[u * NT];
+            if (inv) {
+#pragma unroll
+                for (int u = 0; u < R; u++) v[u] = cswap(v[u]);
+            }
+        } else {
             const bool ok = b * C + c_in < A.W;
             if constexpr (!CHUNK_IN) {
                 const cx<T>* p = A.in + a * A.ia.SA + b * A.ia.SB + c_in * A.ia.cs + (long long)t_in * A.ia.es;
@@ -188,7 +248,9 @@ struct TileOp {
                 for (int u = 0; u < R; u++) v[u] = cswap(v[u]);
             }
         }
-        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, k.exch, k.pp, k.lut_s, twr);
+        // the staging slots are free once the first stage has consumed the registers loaded from them
+        auto hook = [&]() { if constexpr (PF) { if (next_tile >= 0) prefetch(A, k, next_tile); } };
+        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, k.exch, k.pp, k.lut_s, twr, hook);
         {
             if (inv) {
 #pragma unroll
@@ -219,18 +281,22 @@ struct TileOp {
 };
 
 template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, int MINB,
-          bool PINGPONG>
+          bool PINGPONG, bool PF = false>
 __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<T> A)
 {
     static_assert(S::valid(), "bad schedule");
     static_assert(S::NSTAGES > 1 || MAPIN == MAPOUT, "a thread-map change needs an exchange");
-    using Op = TileOp<S, T, C, MAPIN, MAPOUT, TWREG, CHUNK_IN, CHUNK_OUT, PINGPONG>;
+    using Op = TileOp<S, T, C, MAPIN, MAPOUT, TWREG, CHUNK_IN, CHUNK_OUT, PINGPONG, PF>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename Op::Ctx k;
     Op::setup(A, smem_raw, smem_raw + Op::SM::exch_bytes, k);
     cx<T> twr[Op::NTW];
     Op::load_twiddles(k, twr);
-    for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) Op::run(A, k, tile, twr);
+    if (PF && (long long)blockIdx.x < A.ntiles) Op::prefetch(A, k, blockIdx.x);
+    for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const long long next = tile + gridDim.x;
+        Op::run(A, k, tile, twr, next < A.ntiles ? next : -1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -55,7 +55,7 @@ __global__ void check_wave(const double2* buf, long long nlines, int N, long lon
 struct Result { std::string name; float ms; double gbs; double err; int regs; size_t smem; int occ; };
 static std::vector<Result> results;
 static double2 *d_a, *d_b; static double* d_err;
-static const int NX = 512, NY = 512, NZ = 512;
+static int NX = 512, NY = 512, NZ = 512;   // cube edge = transform length of the variant set being run
 static int g_sms = 148;
 static int g_only = -1, g_idx = 0;
 
@@ -65,9 +65,9 @@ void run_variant(const char* name, int pass /*0 Z,1 Y,2 X*/, int ctas_per_sm)
     using T = double;
     if (g_only >= 0 && g_idx++ != g_only) return;
     if (g_only < 0) g_idx++;
-    auto kern = fft_tile_kernel<S, T, C, MAPIN, MAPOUT, TWREG, false, false, MINB, PP>;
+    auto kern = fft_tile_kernel<S, T, C, MAPIN, MAPOUT, TWREG, false, false, MINB, PP, PREFETCH>;
     using SM = TileSmem<S, T, C, PP>;
-    size_t smem = SM::bytes(false);
+    size_t smem = SM::bytes(false) + TileOp<S, T, C, MAPIN, MAPOUT, TWREG, false, false, PP, PREFETCH>::stage_bytes;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, S::T * C, smem));
@@ -174,10 +174,12 @@ __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict_
 
 int main(int argc, char** argv)
 {
-    if (argc > 1) g_only = atoi(argv[1]);
+    int N = argc > 1 ? atoi(argv[1]) : 512;
+    if (argc > 2) g_only = atoi(argv[2]);
+    NX = NY = NZ = N;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     g_sms = prop.multiProcessorCount;
-    printf("device %s sms=%d\n", prop.name, g_sms);
+    printf("device %s sms=%d  cube %d^3 fp64\n", prop.name, g_sms, N);
     size_t n = (size_t)NX * NY * NZ;
     CK(cudaMalloc(&d_a, n * sizeof(double2))); CK(cudaMalloc(&d_b, n * sizeof(double2))); CK(cudaMalloc(&d_err, 8));
     if (g_only < 0) {   // copy roofline reference
@@ -187,40 +189,64 @@ int main(int argc, char** argv)
         for (int i = 0; i < 5; i++) copy_kernel<<<g_sms * 8, 512>>>(d_a, d_b, (long long)n);
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-        printf("copy 2GiB->2GiB: %.3f ms  %.0f GB/s\n", ms, 2.0 * 16.0 * n / ms * 1e-6);
+        printf("copy: %.3f ms  %.0f GB/s\n", ms, 2.0 * 16.0 * n / ms * 1e-6);
     }
-    using S512 = Sched<512, 8, 8, 8, 8>;
-    using S512b = Sched<512, 16, 8, 8, 8>;
-#define V(S, C, MI, MO, TW, PF, MB, pass, cps) run_variant<S, C, MI, MO, TW, PF, MB>(#S " C" #C " tw" #TW " pf" #PF " mb" #MB " cps" #cps, pass, cps)
-    // Z pass
-    V(S512, 2, MAP_T, MAP_T, true, false, 4, 0, 0);
-    // strided copy experiments
-#define CP(C, TT, R, pat, inpl, cps) run_copy<C, TT, R>("C" #C " TT" #TT " R" #R " cps" #cps, pat, inpl, cps)
-    CP(4, 64, 8, 1, true, 2);
-    CP(8, 64, 8, 1, true, 1);
-    CP(8, 32, 8, 1, true, 2);
-    CP(8, 32, 8, 1, true, 4);
-    CP(8, 32, 8, 1, false, 4);
-    CP(16, 16, 8, 1, true, 4);
-    CP(32, 8, 8, 1, true, 4);
-    CP(4, 64, 8, 2, false, 2);
-    CP(8, 64, 8, 2, false, 1);
-    CP(8, 32, 8, 2, false, 4);
-    CP(16, 16, 8, 2, false, 4);
-    CP(32, 8, 8, 2, false, 4);
-    // Y pass
 #define VP(S, C, MI, MO, TW, PF, MB, PP, pass, cps) run_variant<S, C, MI, MO, TW, PF, MB, PP>(#S " C" #C " tw" #TW " pf" #PF " mb" #MB " pp" #PP, pass, cps)
-    VP(S512, 4, MAP_C, MAP_C, true, false, 2, true, 1, 0);
-    VP(S512, 4, MAP_C, MAP_C, false, false, 2, true, 1, 0);
-    VP(S512, 4, MAP_C, MAP_C, false, false, 3, false, 1, 0);
-    VP(S512, 4, MAP_C, MAP_C, true, false, 2, false, 1, 0);
-    VP(S512b, 4, MAP_C, MAP_C, false, false, 4, false, 1, 0);
-    VP(S512b, 8, MAP_C, MAP_C, false, false, 2, false, 1, 0);
-    VP(S512, 8, MAP_C, MAP_C, true, false, 1, true, 1, 0);
-    // X pass
-    VP(S512, 4, MAP_C, MAP_T, true, false, 2, true, 2, 0);
-    VP(S512, 4, MAP_C, MAP_T, false, false, 3, false, 2, 0);
-    VP(S512b, 4, MAP_C, MAP_T, false, false, 4, false, 2, 0);
-    VP(S512b, 8, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+    if (N == 512) {
+        using S512 = Sched<512, 8, 8, 8, 8>;
+        using S512b = Sched<512, 16, 8, 8, 8>;
+        VP(S512, 2, MAP_T, MAP_T, true, false, 4, true, 0, 0);
+        VP(S512, 2, MAP_T, MAP_T, true, true, 3, true, 0, 0);
+        VP(S512b, 8, MAP_C, MAP_C, false, false, 2, false, 1, 0);
+        VP(S512b, 8, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+    } else if (N == 1024) {
+        using S1024 = Sched<1024, 16, 16, 8, 8>;
+        using S1024x = Sched<1024, 8, 8, 8, 8, 2>;
+        // Z
+        VP(S1024, 2, MAP_T, MAP_T, false, false, 4, true, 0, 0);    // current
+        VP(S1024, 2, MAP_T, MAP_T, false, false, 4, false, 0, 0);
+        VP(S1024, 1, MAP_T, MAP_T, false, false, 8, true, 0, 0);
+        VP(S1024, 4, MAP_T, MAP_T, false, false, 2, false, 0, 0);
+        VP(S1024x, 1, MAP_T, MAP_T, true, false, 4, true, 0, 0);
+        VP(S1024x, 1, MAP_T, MAP_T, false, false, 4, true, 0, 0);
+        VP(S1024x, 2, MAP_T, MAP_T, false, false, 2, true, 0, 0);
+        VP(S1024, 2, MAP_T, MAP_T, false, true, 3, false, 0, 0);
+        // Y
+        VP(S1024, 4, MAP_C, MAP_C, false, false, 2, false, 1, 0);   // v0
+        VP(S1024, 8, MAP_C, MAP_C, false, false, 1, false, 1, 0);   // v1
+        VP(S1024x, 4, MAP_C, MAP_C, false, false, 2, false, 1, 0);
+        VP(S1024x, 8, MAP_C, MAP_C, false, false, 1, false, 1, 0);
+        VP(S1024, 4, MAP_C, MAP_C, false, false, 3, false, 1, 0);
+        // X
+        VP(S1024, 4, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+        VP(S1024, 8, MAP_C, MAP_T, false, false, 1, false, 2, 0);
+        VP(S1024x, 4, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+        VP(S1024x, 8, MAP_C, MAP_T, false, false, 1, false, 2, 0);
+    } else if (N == 768) {
+        using S768 = Sched<768, 12, 4, 4, 4, 4, 3>;
+        using S768b = Sched<768, 24, 8, 8, 4, 3>;
+        using S768c = Sched<768, 6, 3, 2, 2, 2, 2, 2, 2, 2, 2>;
+        (void)sizeof(S768c);
+        // Z
+        VP(S768, 2, MAP_T, MAP_T, false, false, 4, true, 0, 0);     // current
+        VP(S768, 2, MAP_T, MAP_T, false, false, 4, false, 0, 0);
+        VP(S768, 4, MAP_T, MAP_T, false, false, 2, false, 0, 0);
+        VP(S768, 1, MAP_T, MAP_T, false, false, 8, true, 0, 0);
+        VP(S768b, 4, MAP_T, MAP_T, false, false, 2, false, 0, 0);
+        VP(S768b, 2, MAP_T, MAP_T, false, false, 4, true, 0, 0);
+        VP(S768b, 8, MAP_T, MAP_T, false, false, 1, false, 0, 0);
+        // Y
+        VP(S768, 4, MAP_C, MAP_C, false, false, 2, false, 1, 0);    // current
+        VP(S768, 8, MAP_C, MAP_C, false, false, 1, false, 1, 0);
+        VP(S768b, 4, MAP_C, MAP_C, false, false, 2, false, 1, 0);
+        VP(S768b, 8, MAP_C, MAP_C, false, false, 1, false, 1, 0);
+        VP(S768b, 8, MAP_C, MAP_C, false, false, 2, false, 1, 0);
+        // X
+        VP(S768, 4, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+        VP(S768, 8, MAP_C, MAP_T, false, false, 1, false, 2, 0);
+        VP(S768b, 4, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+        VP(S768b, 8, MAP_C, MAP_T, false, false, 1, false, 2, 0);
+        VP(S768b, 8, MAP_C, MAP_T, false, false, 2, false, 2, 0);
+    }
     return 0;
 }

@@ -124,6 +124,9 @@ int dfft_execute_stage(dfft_plan plan, int stage);
 /* Host-buffer entry: copies `host_in` (input-slab elements) to bufferDev1, executes, copies the
  * result slab to `host_out`; copies are on the plan's stream (pinned buffers overlap). Synchronous. */
 int dfft_execute_host(dfft_plan plan, const void* host_in, void* host_out);
+/* Same, but returns once the three operations are enqueued on the plan's stream (dfft_synchronize waits).
+ * Two plans driven alternately keep PCIe busy in both directions: plan A's D2H overlaps plan B's H2D. */
+int dfft_execute_host_async(dfft_plan plan, const void* host_in, void* host_out);
 /* milliseconds of the last execute: t[0..3] = t0,t1,t2,t3 as the reference prints them
  * (api.cpp:201; fused stages report 0 for t1 and the *exposed* wait for t2), t[4] = total. */
 int dfft_get_timings(dfft_plan plan, double t_ms[5]);

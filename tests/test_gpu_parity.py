@@ -224,3 +224,36 @@ def test_fused_t0_is_bitwise_the_two_sweep_t0(n, n0):
     ref = np.fft.fftn(A).transpose(1, 2, 0).reshape(-1)
     f = run_slab(n0, n, n, 1, FORWARD, [A.reshape(-1)], flags=dfft.FORCE_FUSE)
     assert np.abs(f[0]["buf2"] - ref).max() <= 1e-12 * np.log2(A.size) * np.abs(ref).max()
+
+
+def test_host_buffer_entry_points_two_plans_in_flight():
+    """dfft_execute_host (synchronous) and dfft_execute_host_async with two plans driven alternately
+    (what bench.py's e2e leg does): every step's pinned host output equals numpy's fftn of its input."""
+    import ctypes
+    n0, n1, n2 = 32, 16, 64
+    cnt = n0 * n1 * n2
+    rng = np.random.default_rng(21)
+    xs = [rng.standard_normal(cnt) + 1j * rng.standard_normal(cnt) for _ in range(2)]
+    refs = [np.fft.fftn(x.reshape(n0, n1, n2)).transpose(1, 2, 0).reshape(-1) for x in xs]
+    dev = torch.device("cuda", 0)
+    bufs = [torch.zeros(cnt, dtype=torch.complex128, device=dev) for _ in range(2)]
+    plans = [dfft.fft_mpi_plan_dft_c2c_3d(n0, n1, n2, b.data_ptr(), None, None, 0, 1, FORWARD) for b in bufs]
+    hin = [dfft.fft_mpi_alloc_local_memory(cnt, dfft.ALLOC_CPU) for _ in range(2)]
+    hout = [dfft.fft_mpi_alloc_local_memory(cnt, dfft.ALLOC_CPU) for _ in range(2)]
+    for k in range(2):
+        ctypes.memmove(hin[k], xs[k].ctypes.data, cnt * 16)
+    plans[0].execute_host(hin[0], hout[0])
+    got = np.empty(cnt, dtype=np.complex128)
+    ctypes.memmove(got.ctypes.data, hout[0], cnt * 16)
+    assert np.abs(got - refs[0]).max() <= 1e-11 * np.abs(refs[0]).max()
+    ctypes.memset(hout[0], 0, cnt * 16)
+    for it in range(6):
+        plans[it % 2].execute_host_async(hin[it % 2], hout[it % 2])
+    for k in range(2):
+        plans[k].synchronize()
+        ctypes.memmove(got.ctypes.data, hout[k], cnt * 16)
+        assert np.abs(got - refs[k]).max() <= 1e-11 * np.abs(refs[k]).max()
+    for k in range(2):
+        plans[k].destroy()
+        dfft.lib().dfft_free_local(hin[k], dfft.ALLOC_CPU)
+        dfft.lib().dfft_free_local(hout[k], dfft.ALLOC_CPU)
