@@ -31,7 +31,7 @@ __all__ = [
     "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
-    "fft_lines", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
+    "fft_lines", "LinesPlan", "length_kind", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
 ]
 
 
@@ -83,6 +83,14 @@ def lib():
     L.dfft_plan_stream.argtypes = [vp]
     L.dfft_plan_stream.restype = vp
     L.dfft_fft_lines.argtypes = [vp, i, ll, ll, ll, ll, ll, i, i]
+    L.dfft_lines_plan_create.argtypes = [i, ll, ll, ll, ll, ll, i, P(vp)]
+    L.dfft_lines_plan_create_2d.argtypes = [i, i, ll, i, P(vp)]
+    L.dfft_lines_execute.argtypes = [vp, vp, i]
+    L.dfft_lines_synchronize.argtypes = [vp]
+    L.dfft_lines_destroy.argtypes = [vp]
+    L.dfft_lines_stream.argtypes = [vp]
+    L.dfft_lines_stream.restype = vp
+    L.dfft_length_kind.argtypes = [i, i]
     L.dfft_memcpy.argtypes = [vp, vp, ctypes.c_size_t, i]
     _lib = L
     return L
@@ -98,6 +106,11 @@ def supported_lengths(precision=DOUBLE):
     arr = (ctypes.c_int * n)()
     lib().dfft_supported_lengths(precision, arr, n)
     return list(arr)
+
+
+def length_kind(n, precision=DOUBLE):
+    """2 = tuned kernel, 1 = run-time-scheduled kernel (2..13-smooth lengths), 0 = unsupported."""
+    return int(lib().dfft_length_kind(n, precision))
 
 
 def getMaxDataCount(n0, n1, n2, totalDevCount, isLastDevice):
@@ -276,6 +289,34 @@ def memcpy_htod(dev_ptr, host_ptr, nbytes):
 
 def memcpy_dtoh(host_ptr, dev_ptr, nbytes):
     _check(lib().dfft_memcpy(host_ptr, dev_ptr, nbytes, 2), "dfft_memcpy")
+
+
+class LinesPlan:
+    """templateFFT engine surface (templateFFT.h:361-365): initializeFFT -> LinesPlan(...), launchFFTKernel -> execute,
+    deleteFFT -> destroy.  Batched 1-D lines (contiguous or strided) or, with `two_d=(nx, ny, batch)`, batched 2-D."""
+
+    def __init__(self, n=None, stride=1, nlines=0, inner=0, inner_dist=0, outer_dist=0, precision=DOUBLE, two_d=None):
+        h = ctypes.c_void_p()
+        if two_d is not None:
+            _check(lib().dfft_lines_plan_create_2d(two_d[0], two_d[1], two_d[2], precision, ctypes.byref(h)), "dfft_lines_plan_create_2d")
+        else:
+            _check(lib().dfft_lines_plan_create(n, stride, nlines, inner, inner_dist, outer_dist, precision, ctypes.byref(h)), "dfft_lines_plan_create")
+        self.handle = h
+
+    def execute(self, ptr, direction):
+        _check(lib().dfft_lines_execute(self.handle, ptr, direction), "dfft_lines_execute")
+
+    def synchronize(self):
+        _check(lib().dfft_lines_synchronize(self.handle), "dfft_lines_synchronize")
+
+    @property
+    def stream(self):
+        return lib().dfft_lines_stream(self.handle)
+
+    def destroy(self):
+        if self.handle:
+            lib().dfft_lines_destroy(self.handle)
+            self.handle = None
 
 
 def fft_lines(ptr, n, stride, nlines, inner, inner_dist, outer_dist, direction, precision=DOUBLE):

@@ -22,8 +22,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 
-LIB_SOURCES = ["dfft_api.cu", "dfft_kernels_common.cu", "dfft_kernels_f64.cu", "dfft_kernels_f32.cu"]
-HEADERS = ["fft_core.cuh", "fft_passes.cuh", "dfft_kernels.cuh", "dfft_kernels_inst.cuh", os.path.join("..", "..", "include", "dfft.h")]
+LIB_SOURCES = ["dfft_api.cu", "dfft_kernels_common.cu", "dfft_kernels_generic.cu", "dfft_kernels_f64.cu", "dfft_kernels_f32.cu"]
+HEADERS = ["fft_core.cuh", "fft_passes.cuh", "fft_generic.cuh", "dfft_kernels.cuh", "dfft_kernels_inst.cuh", os.path.join("..", "..", "include", "dfft.h")]
 
 
 def _newer(target, deps):
@@ -63,6 +63,11 @@ def build(force: bool = False, tools: bool = False, verbose: bool = False) -> st
     if os.path.exists(drv) and (force or _newer(DRIVER, [drv, LIB, os.path.join(HERE, "..", "include", "fft_mpi_3d_api.h")])):
         _run([NVCC] + ARCH + ["-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", "-I", os.path.join(HERE, "..", "include"), drv, "-o", DRIVER,
               "-L", HERE, "-ldfft", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-lpthread"])
+    bdrv = os.path.join(HERE, "driver", "batchFFT.cpp")
+    bout = os.path.join(HERE, "batchFFT")
+    if os.path.exists(bdrv) and (force or _newer(bout, [bdrv, LIB, os.path.join(HERE, "..", "include", "dfft.h")])):
+        _run([NVCC] + ARCH + ["-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", "-I", os.path.join(HERE, "..", "include"), bdrv, "-o", bout,
+              "-L", HERE, "-ldfft", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     if tools:
         kb = os.path.join(CSRC, "tools", "kbench.cu")
         out = os.path.join(CSRC, "tools", "kbench")

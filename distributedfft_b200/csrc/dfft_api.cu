@@ -49,6 +49,13 @@ static int fail(int code, const char* fmt, ...)
 extern "C" const char* dfft_last_error(void) { return g_err.c_str(); }
 extern "C" int dfft_version(void) { return 100; }
 
+extern "C" int dfft_length_kind(int n, int precision)
+{
+    if (n < 1 || n > (1 << 20) || (precision != DFFT_DOUBLE && precision != DFFT_FLOAT)) return 0;
+    const SizeEntry* e = find_size_entry(n, precision);
+    return !e ? 0 : (e->gen ? 1 : 2);
+}
+
 extern "C" int dfft_supported_lengths(int precision, int* lengths, int max_lengths)
 {
     std::vector<int> v;
@@ -591,6 +598,7 @@ template <typename T> struct Pass {
     static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a)
     {
         a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
+        a.gen = e->gen;
         const int axis = kind == PK_Z ? 0 : (kind == PK_Y || kind == PK_Y_CO || kind == PK_Y_CI ? 1 : 2);
         cudaEventRecord(p->pev[axis][0], p->stream);
         cudaError_t err = e->launch[kind](&a, p->sms, p->stream);
@@ -1019,50 +1027,156 @@ extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode !=
 extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }
 
 // ------------------------------------------------------------------------------------------------
-// batched local transforms
+// batched local transforms: plan / launch / delete, the templateFFT engine surface
+// (3dmpifft_opt/include/templateFFT.h:361-365 initializeFFT / launchFFTKernel / deleteFFT)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-static int fft_lines_impl(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
-                          long long outer_dist, int direction, const SizeEntry* e)
-{
-    int sms = 0, dev = 0;
-    CU(cudaGetDevice(&dev));
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TileArgs<T> a{};
-    a.in = (const cx<T>*)data; a.out = (cx<T>*)data;
-    a.inv = direction == DFFT_BACKWARD;
+struct LinePass {
+    const SizeEntry* e = nullptr;
+    int kind = PK_Z;
     void* lut = nullptr;
-    int kind;
+    Affine ia{};
+    int G = 0, W = 0;
+    long long ntiles = 0;
+};
+struct dfft_lines_plan_s {
+    int prec = 0, device = 0, sms = 148, npass = 0;
+    LinePass pass[2];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool timed = false;
+};
+
+template <typename T> static void upload_lut_e(void** dst, const SizeEntry* e, bool contiguous)
+{
+    if (contiguous) upload_lut<T>(dst, e->z_nstages, e->z_rad);
+    else upload_lut<T>(dst, e->s_nstages, e->s_rad);
+}
+
+static int make_line_pass(LinePass& lp, int n, long long stride, long long nlines, long long inner, long long inner_dist, long long outer_dist,
+                          int precision)
+{
+    const SizeEntry* e = find_size_entry(n, precision);
+    if (!e) return fail(DFFT_EUNSUPPORTED, "unsupported length %d", n);
+    lp.e = e;
     if (stride == 1) {
         if (inner_dist != n || (inner != nlines && outer_dist != inner * n)) return fail(DFFT_EUNSUPPORTED, "contiguous lines must be densely packed");
-        upload_lut<T>(&lut, e->z_nstages, e->z_rad);
         const int C = e->z_C;
-        a.G = (int)cdiv(nlines, C); a.W = (int)nlines; a.ntiles = a.G;
-        a.ia = Affine{0, (long long)C * n, n, 1};
-        kind = PK_Z;
+        lp.G = (int)cdiv(nlines, C); lp.W = (int)std::min<long long>(nlines, 0x7fffffff); lp.ntiles = lp.G;
+        lp.ia = Affine{0, (long long)C * n, n, 1};
+        lp.kind = PK_Z;
     } else {
         if (inner_dist != 1 || inner < 1 || nlines % inner) return fail(DFFT_EUNSUPPORTED, "strided lines must be columns (inner_dist == 1)");
-        upload_lut<T>(&lut, e->s_nstages, e->s_rad);
         const int C = e->s_C;
-        a.G = (int)cdiv(inner, C); a.W = (int)inner; a.ntiles = (nlines / inner) * a.G;
-        a.ia = Affine{outer_dist, C, 1, stride};
-        kind = PK_Y;
+        lp.G = (int)cdiv(inner, C); lp.W = (int)inner; lp.ntiles = (nlines / inner) * lp.G;
+        lp.ia = Affine{outer_dist, C, 1, stride};
+        lp.kind = PK_Y;
     }
-    a.oa = a.ia; a.lut = (const cx<T>*)lut;
-    cudaError_t err = e->launch[kind](&a, sms, 0);
-    if (err == cudaSuccess) err = cudaDeviceSynchronize();
-    cudaFree(lut);
-    if (err != cudaSuccess) return fail(DFFT_ECUDA, "fft_lines failed: %s", cudaGetErrorString(err));
+    if (precision == DFFT_DOUBLE) upload_lut_e<double>(&lp.lut, e, stride == 1);
+    else upload_lut_e<float>(&lp.lut, e, stride == 1);
+    if (cudaGetLastError() != cudaSuccess || !lp.lut) return fail(DFFT_ECUDA, "twiddle table upload failed");
     return 0;
 }
+
+static int lines_plan_common(dfft_lines_plan p, int precision)
+{
+    p->prec = precision;
+    CU(cudaGetDevice(&p->device));
+    CU(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto& e : p->ev) CU(cudaEventCreate(&e));
+    return 0;
+}
+
+extern "C" int dfft_lines_destroy(dfft_lines_plan p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (int i = 0; i < 2; i++) if (p->pass[i].lut) cudaFree(p->pass[i].lut);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    cudaGetLastError();
+    delete p;
+    return 0;
+}
+
+extern "C" int dfft_lines_plan_create(int n, long long stride, long long nlines, long long inner, long long inner_dist, long long outer_dist,
+                                      int precision, dfft_lines_plan* out)
+{
+    if (!out) return fail(DFFT_EINVAL, "null plan pointer");
+    *out = nullptr;
+    if (n < 1 || nlines < 0 || stride < 1 || (precision != DFFT_DOUBLE && precision != DFFT_FLOAT)) return fail(DFFT_EINVAL, "bad arguments");
+    dfft_lines_plan p = new dfft_lines_plan_s;
+    int rc = lines_plan_common(p, precision);
+    if (!rc) rc = make_line_pass(p->pass[0], n, stride, nlines, inner, inner_dist, outer_dist, precision);
+    if (rc) { dfft_lines_destroy(p); return rc; }
+    p->npass = 1;
+    *out = p;
+    return 0;
+}
+
+/* batch of 2-D transforms, nx fastest: the reference's FFTdim = 2 application (Test_2D.cpp: size = {X, Y, Z}) */
+extern "C" int dfft_lines_plan_create_2d(int nx, int ny, long long batch, int precision, dfft_lines_plan* out)
+{
+    if (!out) return fail(DFFT_EINVAL, "null plan pointer");
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || batch < 0 || (precision != DFFT_DOUBLE && precision != DFFT_FLOAT)) return fail(DFFT_EINVAL, "bad arguments");
+    dfft_lines_plan p = new dfft_lines_plan_s;
+    int rc = lines_plan_common(p, precision);
+    if (!rc) rc = make_line_pass(p->pass[0], nx, 1, (long long)ny * batch, (long long)ny * batch, nx, 0, precision);
+    if (!rc) rc = make_line_pass(p->pass[1], ny, nx, (long long)nx * batch, nx, 1, (long long)nx * ny, precision);
+    if (rc) { dfft_lines_destroy(p); return rc; }
+    p->npass = 2;
+    *out = p;
+    return 0;
+}
+
+template <typename T> static int lines_execute_impl(dfft_lines_plan p, void* data, int direction)
+{
+    CU(cudaEventRecord(p->ev[0], p->stream));
+    for (int k = 0; k < p->npass; k++) {
+        const LinePass& lp = p->pass[direction == DFFT_BACKWARD ? p->npass - 1 - k : k];
+        if (lp.ntiles <= 0) continue;
+        TileArgs<T> a{};
+        a.in = (const cx<T>*)data; a.out = (cx<T>*)data; a.lut = (const cx<T>*)lp.lut;
+        a.ia = lp.ia; a.oa = lp.ia; a.G = lp.G; a.W = lp.W; a.ntiles = lp.ntiles;
+        a.inv = direction == DFFT_BACKWARD; a.gen = lp.e->gen;
+        cudaError_t err = lp.e->launch[lp.kind](&a, p->sms, p->stream);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "line pass launch failed: %s", cudaGetErrorString(err));
+    }
+    CU(cudaEventRecord(p->ev[1], p->stream));
+    p->timed = true;
+    return 0;
+}
+
+extern "C" int dfft_lines_execute(dfft_lines_plan p, void* data, int direction)
+{
+    if (!p || !data || (direction != DFFT_FORWARD && direction != DFFT_BACKWARD)) return fail(DFFT_EINVAL, "bad arguments");
+    CU(cudaSetDevice(p->device));
+    return p->prec == DFFT_DOUBLE ? lines_execute_impl<double>(p, data, direction) : lines_execute_impl<float>(p, data, direction);
+}
+
+extern "C" int dfft_lines_synchronize(dfft_lines_plan p)
+{
+    if (!p) return fail(DFFT_EINVAL, "null plan");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" void* dfft_lines_stream(dfft_lines_plan p) { return p ? (void*)p->stream : nullptr; }
 
 extern "C" int dfft_fft_lines(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
                               long long outer_dist, int direction, int precision)
 {
     if (!data || n < 1 || nlines < 0 || stride < 1) return fail(DFFT_EINVAL, "bad arguments");
-    const SizeEntry* e = find_size_entry(n, precision);
-    if (!e) return fail(DFFT_EUNSUPPORTED, "unsupported length %d", n);
+    if (direction != DFFT_FORWARD && direction != DFFT_BACKWARD) return fail(DFFT_EINVAL, "direction must be +1 or -1");
     if (nlines == 0) return 0;
-    return precision == DFFT_DOUBLE ? fft_lines_impl<double>(data, n, stride, nlines, inner, inner_dist, outer_dist, direction, e)
-                                    : fft_lines_impl<float>(data, n, stride, nlines, inner, inner_dist, outer_dist, direction, e);
+    dfft_lines_plan p = nullptr;
+    int rc = dfft_lines_plan_create(n, stride, nlines, inner, inner_dist, outer_dist, precision, &p);
+    if (rc) return rc;
+    rc = dfft_lines_execute(p, data, direction);
+    if (!rc) rc = dfft_lines_synchronize(p);
+    dfft_lines_destroy(p);
+    return rc;
 }

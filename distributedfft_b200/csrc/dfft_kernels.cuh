@@ -37,15 +37,19 @@ struct SizeEntry {
     int variant;          // 0 = default; > 0 = alternate tuning of the same length, selected with DFFT_VARIANT (experiments)
     int prec;             // 0 = double, 1 = float
     int z_C, s_C, p_C, x_C;   // lines per tile: contiguous (Z), strided local (Y), strided with peer/packed store, X passes
-    int z_nstages, z_rad[12];
-    int s_nstages, s_rad[12];
-    int x_nstages, x_rad[12];
+    int z_nstages, z_rad[24];
+    int s_nstages, s_rad[24];
+    int x_nstages, x_rad[24];
     PassLaunchFn launch[PK_COUNT];
     int f_zC, f_zCp;      // lines per contiguous tile inside the fused kernels (same CTA size as the strided role; p: peer-store kind)
     FusedLaunchFn fused[FK_COUNT];   // valid for square planes (N1 == N2 == N): both roles come from this entry
+    const void* gen;      // run-time schedule (GenSched) of a generic-length entry, nullptr for tuned lengths
 };
 
+// tuned entry if the length is in the table, else a generic (run-time scheduled) entry for 2..13-smooth lengths,
+// else nullptr.  DFFT_GENERIC=1 forces the generic kernel (tests).
 const SizeEntry* find_size_entry(int N, int prec);
+const SizeEntry* generic_size_entry(int N, int prec);
 void list_sizes(int prec, std::vector<int>& out);
 
 // twiddle table of a radix list, layout of Sched::lut_off(): per stage s >= 1,

@@ -19,6 +19,8 @@ static std::vector<SizeEntry>& table()
 
 const SizeEntry* find_size_entry(int N, int prec)
 {
+    const char* gen = getenv("DFFT_GENERIC");
+    if (gen && atoi(gen) != 0) return generic_size_entry(N, prec);
     const char* env = getenv("DFFT_VARIANT");
     const int want = env ? atoi(env) : 0;
     const SizeEntry* def = nullptr;
@@ -27,6 +29,7 @@ const SizeEntry* find_size_entry(int N, int prec)
         if (e.variant == want) return &e;
         if (e.variant == 0) def = &e;
     }
+    if (!def) return generic_size_entry(N, prec);
     return def;
 }
 

@@ -42,6 +42,7 @@ template <typename T> struct TileArgs {
     int inv;               // 1: inverse transform (e^{+i..}), unnormalised
     int do_scale;
     ChunkTab ci, co;       // used when CHUNK_IN / CHUNK_OUT
+    const void* gen;       // host pointer to the GenSched of a generic-length entry (read by its launcher only)
 };
 
 template <class S, typename T, int C, bool PINGPONG>

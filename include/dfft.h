@@ -69,7 +69,12 @@ typedef int (*dfft_allgather_fn)(void* ctx, const void* send, void* recv, size_t
 /* -- library ------------------------------------------------------------------------------- */
 const char* dfft_last_error(void);
 int dfft_version(void);
-/* number of supported transform lengths for a precision; fills `lengths` (may be NULL) */
+/* 2: `n` has a tuned kernel; 1: handled by the run-time-scheduled kernel (any length whose prime factors are
+ * in {2,3,5,7,11,13} -- the set templateFFT accepts, templateFFT.cpp:3956-3964 -- up to 6400 points in double and
+ * 12800 in float, i.e. while two copies of a line fit in shared memory); 0: unsupported (other primes, or longer:
+ * the reference switches to multi-upload passes there, templateFFT.cpp:4007-4106, which this library does not have) */
+int dfft_length_kind(int n, int precision);
+/* number of TUNED transform lengths for a precision; fills `lengths` (may be NULL) */
 int dfft_supported_lengths(int precision, int* lengths, int max_lengths);
 
 /* -- slab bookkeeping ---------------------------------------------------------------------- */
@@ -153,12 +158,24 @@ int dfft_cleanup(void);
  * kind 1 = host->device, 2 = device->host, 0 = default (UVA) */
 int dfft_memcpy(void* dst, const void* src, size_t bytes, int kind);
 
-/* -- batched local transforms (the templateFFT engine surface, opt/include/templateFFT.h:361-365:
- *    initializeFFT / launchFFTKernel on a contiguous or strided axis), used by per-axis parity tests
- *    and the batched 1-D benchmark.  Transforms `nlines` lines of length n in place:
- *    line l starts at data + (l / inner) * outer_dist + (l % inner) * inner_dist (in elements),
- *    points are `stride` elements apart.  Supported shapes: stride == 1 (inner_dist == n), or
- *    stride > 1 with inner_dist == 1 (columns of a row-major matrix).  Synchronous. */
+/* -- batched local transforms: the templateFFT engine surface (3dmpifft_opt/include/templateFFT.h:361-365) -----
+ *    initializeFFT(app, config)   -> dfft_lines_plan_create / dfft_lines_plan_create_2d
+ *    launchFFTKernel(app, inverse)-> dfft_lines_execute (asynchronous on the plan's stream, in place)
+ *    deleteFFT(app)               -> dfft_lines_destroy
+ *    Line l starts at data + (l / inner) * outer_dist + (l % inner) * inner_dist (in elements), points are
+ *    `stride` elements apart.  Supported shapes: stride == 1 with densely packed lines (inner_dist == n), or
+ *    stride > 1 with inner_dist == 1 (columns of row-major matrices: `inner` columns per matrix, matrices
+ *    `outer_dist` apart).  The 2-D plan transforms `batch` row-major ny x nx matrices (nx fastest), the
+ *    reference's FFTdim = 2 application (templateFFT/batchTest/Test_2D.cpp). */
+typedef struct dfft_lines_plan_s* dfft_lines_plan;
+int dfft_lines_plan_create(int n, long long stride, long long nlines, long long inner, long long inner_dist,
+                           long long outer_dist, int precision, dfft_lines_plan* plan);
+int dfft_lines_plan_create_2d(int nx, int ny, long long batch, int precision, dfft_lines_plan* plan);
+int dfft_lines_execute(dfft_lines_plan plan, void* data, int direction);
+int dfft_lines_synchronize(dfft_lines_plan plan);
+void* dfft_lines_stream(dfft_lines_plan plan);
+int dfft_lines_destroy(dfft_lines_plan plan);
+/* one-shot convenience (plan + execute + synchronize + destroy), used by the per-axis parity tests */
 int dfft_fft_lines(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
                    long long outer_dist, int direction, int precision);
 

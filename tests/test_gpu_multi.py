@@ -34,7 +34,7 @@ def co():
 
 MODES = {"p2p": dfft.EXCHANGE_P2P, "nccl": dfft.EXCHANGE_NCCL, "staged": dfft.EXCHANGE_STAGED}
 # (P, n0, n1, n2): even and uneven (short last slab in x and/or y) splits
-CASES = [(2, 16, 16, 16), (2, 6, 9, 9), (4, 12, 10, 10), (2, 10, 9, 4), (2, 64, 48, 96), (4, 12, 10, 24), (4, 64, 64, 64), (8, 64, 64, 64), (8, 100, 125, 8),
+CASES = [(2, 4, 1024, 1024), (2, 6, 768, 768), (2, 30, 21, 10), (2, 16, 16, 16), (2, 6, 9, 9), (4, 12, 10, 10), (2, 10, 9, 4), (2, 64, 48, 96), (4, 12, 10, 24), (4, 64, 64, 64), (8, 64, 64, 64), (8, 100, 125, 8),
          (8, 24, 48, 16)]
 
 
@@ -94,10 +94,9 @@ def test_multi_gpu_spectrum_and_round_trip(co, P):
     assert np.abs(B - A).max() <= 1e-11
 
 
-@pytest.mark.parametrize("P", [2, 4, 8])
-def test_multi_gpu_float32(P):
+@pytest.mark.parametrize("P,n0,n1,n2", [(2, 96, 48, 64), (4, 96, 48, 64), (8, 96, 48, 64), (2, 4, 768, 768), (2, 4, 1024, 1024), (2, 22, 15, 15)])
+def test_multi_gpu_float32(P, n0, n1, n2):
     need(P)
-    n0, n1, n2 = 96, 48, 64
     ns = NumpySlab(n0, n1, n2, P)
     rng = np.random.default_rng(P)
     A = (rng.random((n0, n1, n2)) + 1j * rng.random((n0, n1, n2))).astype(np.complex64)

@@ -257,3 +257,123 @@ def test_host_buffer_entry_points_two_plans_in_flight():
         plans[k].destroy()
         dfft.lib().dfft_free_local(hin[k], dfft.ALLOC_CPU)
         dfft.lib().dfft_free_local(hout[k], dfft.ALLOC_CPU)
+
+
+GENERIC_LENGTHS = [2, 3, 5, 7, 11, 13, 15, 30, 77, 143, 360, 1001, 2187, 3000, 3125, 6400]
+
+
+@pytest.mark.parametrize("precision", [dfft.DOUBLE, dfft.FLOAT])
+def test_generic_lengths_per_axis(co, precision):
+    """Lengths without a tuned kernel run on the run-time-scheduled kernel (fft_generic.cuh): every
+    2..13-smooth length the reference's generator accepts (templateFFT.cpp:3956-3964), contiguous and
+    strided, forward and inverse, against numpy's pocketfft."""
+    tol = 1e-12 if precision == dfft.DOUBLE else 3e-6
+    rng = np.random.default_rng(17)
+    for n in GENERIC_LENGTHS:
+        assert dfft.length_kind(n, precision) == 1, n
+        a = (rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))).astype(CDT[precision][0])
+        b = (rng.standard_normal((2, n, 11)) + 1j * rng.standard_normal((2, n, 11))).astype(CDT[precision][0])
+        for direction in (FORWARD, BACKWARD):
+            f = np.fft.fft if direction == FORWARD else (lambda x, axis: np.fft.ifft(x, axis=axis) * x.shape[axis])
+            ref = f(a.astype(np.complex128), axis=1)
+            t = _dev_array(a.reshape(-1), precision)
+            dfft.fft_lines(t.data_ptr(), n, 1, 5, 5, n, 5 * n, direction, precision)
+            err = np.abs(t.cpu().numpy().reshape(5, n) - ref).max() / np.abs(ref).max()
+            assert err <= tol * max(1.0, np.log2(n)), (n, "contig", direction, err)
+            ref = f(b.astype(np.complex128), axis=1)
+            t = _dev_array(b.reshape(-1), precision)
+            dfft.fft_lines(t.data_ptr(), n, 11, 2 * 11, 11, 1, n * 11, direction, precision)
+            err = np.abs(t.cpu().numpy().reshape(2, n, 11) - ref).max() / np.abs(ref).max()
+            assert err <= tol * max(1.0, np.log2(n)), (n, "strided", direction, err)
+    assert dfft.length_kind(17, precision) == 0 and dfft.length_kind(6561 * 2, precision) == 0
+
+
+def test_golden_11_point_dft_and_box_all_axes():
+    """The reference tree's pen-and-paper vectors through the C ABI: 11-point DFT of 1..11
+    (test_units_stock.cpp:229-255) and the 2x3x4 box along every axis (test_units_nompi.cpp:136-190)."""
+    with open(os.path.join(HERE, "golden", "heffte_vectors.json")) as f:
+        gold = json.load(f)
+    c = lambda v: np.asarray(v)[..., 0] + 1j * np.asarray(v)[..., 1]
+    x11 = np.arange(1, 12, dtype=np.complex128)
+    t = _dev_array(x11, dfft.DOUBLE)
+    dfft.fft_lines(t.data_ptr(), 11, 1, 1, 1, 11, 11, FORWARD)
+    assert np.abs(c(gold["dft11_input"]).reshape(-1) - x11).max() == 0
+    assert np.abs(t.cpu().numpy() - c(gold["dft11_output"]).reshape(-1)).max() < 1e-11
+    shape = tuple(gold["box_shape_c_order"])   # (4, 3, 2): axis 2 fastest
+    x = c(gold["box_input"]).reshape(shape)
+    # axis 2 (length 2, contiguous), axis 1 (length 3, stride 2), axis 0 (length 4, stride 6)
+    for key, n, stride, nlines, inner, inner_dist, outer in (("box_fft_dim0_axis2", 2, 1, 12, 12, 2, 24),
+                                                           ("box_fft_dim1_axis1", 3, 2, 8, 2, 1, 6),
+                                                           ("box_fft_dim2_axis0", 4, 6, 6, 6, 1, 24)):
+        t = _dev_array(x.reshape(-1), dfft.DOUBLE)
+        dfft.fft_lines(t.data_ptr(), n, stride, nlines, inner, inner_dist, outer, FORWARD)
+        assert np.abs(t.cpu().numpy().reshape(shape) - c(gold[key]).reshape(shape)).max() < 1e-11, key
+
+
+@pytest.mark.parametrize("n0,n1,n2", [(15, 22, 26), (6, 35, 33), (64, 64, 64)])
+def test_generic_kernel_3d_forward_backward(co, n0, n1, n2, monkeypatch):
+    """Whole slab path on the run-time-scheduled kernel: lengths without tuned kernels, and (DFFT_GENERIC=1) the
+    generic kernel on a tuned size must agree with the tuned kernels to rounding."""
+    rng = np.random.default_rng(n0 + n1)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    ref = np.fft.fftn(A).transpose(1, 2, 0).reshape(-1)
+    if (n0, n1, n2) == (64, 64, 64):
+        monkeypatch.setenv("DFFT_GENERIC", "1")
+    res = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)])
+    assert np.abs(res[0]["buf2"] - ref).max() <= 1e-12 * np.log2(A.size) * np.abs(ref).max()
+    back = run_slab(n0, n1, n2, 1, BACKWARD, [ref])
+    assert np.abs(back[0]["buf2"] / A.size - A.reshape(-1)).max() <= 1e-11
+
+
+def test_lines_plan_2d_and_reuse():
+    """The engine surface (initializeFFT / launchFFTKernel / deleteFFT -> LinesPlan): a batched 2-D plan reused for
+    several launches, forward then inverse, against numpy's fft2."""
+    nx, ny, batch = 64, 48, 5
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((batch, ny, nx)) + 1j * rng.standard_normal((batch, ny, nx))
+    ref = np.fft.fft2(a, axes=(1, 2))
+    plan = dfft.LinesPlan(two_d=(nx, ny, batch))
+    t = _dev_array(a.reshape(-1), dfft.DOUBLE)
+    plan.execute(t.data_ptr(), FORWARD); plan.synchronize()
+    assert np.abs(t.cpu().numpy().reshape(batch, ny, nx) - ref).max() <= 1e-12 * 12 * np.abs(ref).max()
+    plan.execute(t.data_ptr(), BACKWARD); plan.synchronize()
+    assert np.abs(t.cpu().numpy().reshape(batch, ny, nx) / (nx * ny) - a).max() <= 1e-12
+    t2 = _dev_array(a.reshape(-1), dfft.DOUBLE)
+    plan.execute(t2.data_ptr(), FORWARD); plan.synchronize()
+    assert np.abs(t2.cpu().numpy().reshape(batch, ny, nx) - ref).max() <= 1e-12 * 12 * np.abs(ref).max()
+    plan.destroy()
+
+
+def test_batch_benchmark_driver_surface(tmp_path):
+    """batchFFT 1d|2d X Y Z num_iter printResult: stdout lines and CSV columns of templateFFT/batchTest/Test_1D.cpp:139-176
+    and Test_2D.cpp (runTest1D_opt.sh:4 header), round-trip error on the ramp input."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "distributedfft_b200", "batchFFT")
+    assert os.path.exists(exe), "batchFFT was not built"
+    for mode, args, dims in (("1d", ["1024", "1", "1"], "1024x65536x1"), ("2d", ["256", "128", "1"], "256x128x2048")):
+        csv = tmp_path / f"batch_{mode}.csv"
+        r = subprocess.run([exe, mode] + args + ["3", "1", str(csv)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"1 - FFT + iFFT C2C {mode.upper()} in double precision LUT" in r.stdout
+        m = re.search(r"FFT: (\S+) Buffer: ([0-9.]+) MB avg_hip_time: ([0-9.]+) ms Gflops: ([0-9.]+) num_iter: 3", r.stdout)
+        assert m and m.group(1) == dims and float(m.group(2)) == 1024.0, r.stdout
+        err = float(re.search(r"Max error: (\S+)", r.stdout).group(1))
+        assert err < 1e-6      # ramp values reach 6.7e7; the reference prints 3.5e-13..6.7e-11 relative to far smaller batches
+        assert "element 0 input:  (1,0)" in r.stdout
+        cols = csv.read_text().strip().split(",")
+        assert len(cols) == 9 and cols[0] == args[0]
+
+
+def test_compute_sanitizer_memcheck_and_racecheck():
+    """the driver on a small cube under compute-sanitizer (memcheck, racecheck) is clean."""
+    import shutil
+    import subprocess
+    cs = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(cs):
+        pytest.skip("compute-sanitizer not installed")
+    exe = os.path.join(os.path.dirname(HERE), "distributedfft_b200", "distFFT")
+    for tool in ("memcheck", "racecheck"):
+        r = subprocess.run([cs, "--tool", tool, "--error-exitcode", "7", exe, "16", "16", "16", "1"], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (tool, r.stdout[-3000:], r.stderr[-2000:])
+        assert "ERROR SUMMARY: 0 errors" in r.stdout or "RACECHECK SUMMARY: 0 hazards" in r.stdout, (tool, r.stdout[-1500:])

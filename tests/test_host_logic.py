@@ -61,7 +61,7 @@ def test_fft_mpi_init_device_policy():
 
 def test_plan_rejects_bad_arguments_without_touching_a_gpu():
     with pytest.raises(dfft.DfftError, match="unsupported transform length"):
-        dfft.fft_mpi_plan_dft_c2c_3d(11, 16, 16, 1, 2, None, 0, 1, FORWARD)
+        dfft.fft_mpi_plan_dft_c2c_3d(17, 16, 16, 1, 2, None, 0, 1, FORWARD)
     with pytest.raises(dfft.DfftError, match="communicator"):
         dfft.fft_mpi_plan_dft_c2c_3d(16, 16, 16, 1, 2, None, 0, 2, FORWARD)
     with pytest.raises(dfft.DfftError, match="empty last slab"):
