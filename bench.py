@@ -162,8 +162,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "3D C2C forward FFT GFlops/s (5*N^3*log2(N^3)/t)", "value": val, "unit": "GFlops/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n}x{n}x{n} C2C double forward, CPU oracle port of the reference path (no GPU)",
-                   "host_threads": r["threads"]},
+        "config": {"workload": f"{n}x{n}x{n} C2C double forward, slab decomposition over {args.gpus} GPU(s)",
+                   "arm": "CPU oracle port of the reference path (oracle/oracle_fft.c, OpenMP; the reference itself needs HIP/rocFFT/MPI)",
+                   "host_threads": r["threads"], "exchange": "none (one process)", "parallelism": "cpu"},
         "cpu_baseline": {"value": val, "unit": "GFlops/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": val, "unit": "GFlops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
