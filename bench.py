@@ -239,6 +239,8 @@ def run_dfft_arm(args):
         flags |= dfft.NO_FUSE
     if args.fuse:
         flags |= dfft.FORCE_FUSE
+    if args.overlap:
+        flags |= dfft.OVERLAP_X
     plan = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tin.data_ptr(), tout.data_ptr(), comm, rank, P, dfft.FORWARD, prec, flags)
     stream = torch.cuda.ExternalStream(plan.stream, device=dev)
 
@@ -317,7 +319,11 @@ def run_dfft_arm(args):
     M = float(n) ** 3 / P
     peak, peak_src = measured_peak()
     slab_bytes = 2.0 * esz * M                      # one read + one write of the local slab (per axis pass)
-    if plan.fused:
+    if plan.overlapped:
+        # the whole forward transform of a device is ONE kernel (Z, Y with peer stores, X behind arrival flags): compulsory
+        # HBM traffic = slab read + intermediate write-back + receive-buffer read + result write = 4*E*M
+        kernels = [("whole forward transform (fft_fused3_kernel: Z + Y/peer-store + X roles)", passes_avg[0], 2 * slab_bytes, 3 * slab_bytes, "fwd_overlapped")]
+    elif plan.fused:
         # t0 is ONE kernel doing the Z and Y passes with the intermediate resident in L2: its compulsory HBM
         # traffic is one read + one write of the slab (2*E*M); by SURVEY 8d's per-pass convention it does 4*E*M.
         kernels = [("t0 fused Z+Y (fft_fused2_kernel: contiguous + strided role, intermediate L2-resident)", passes_avg[0], slab_bytes, 2 * slab_bytes, "t0_fused"),
@@ -343,9 +349,9 @@ def run_dfft_arm(args):
         "config": {"workload": f"{n}x{n}x{n} C2C {args.precision} forward, slab decomposition over {P} GPU(s)",
                    "exchange": {1: "p2p-fused", 2: "nccl", 3: "staged"}[plan.exchange] if P > 1 else "none",
                    "l2": "inputs (%.2f GiB per GPU) exceed the 126 MB L2; no flush needed" % (M * esz / 2 ** 30),
-                   "parallelism": f"slab{P}", "t0": "fused-L2" if plan.fused else "two-sweep"},
+                   "parallelism": f"slab{P}", "t0": "overlapped-single-kernel" if plan.overlapped else ("fused-L2" if plan.fused else "two-sweep")},
         "stage_ms": {"t0": stage[0], "t1": stage[1], "t2": stage[2], "t3": stage[3], "total": stage[4]},
-        "pass_ms": ({"t0_fused_zy": passes_avg[0], "x": passes_avg[2]} if plan.fused else
+        "pass_ms": ({"forward_single_kernel": passes_avg[0]} if plan.overlapped else {"t0_fused_zy": passes_avg[0], "x": passes_avg[2]} if plan.fused else
                     {"z": passes_avg[0], "y": passes_avg[1], "x": passes_avg[2]}),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
@@ -391,6 +397,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large sizes: 4 pinned slabs per rank)")
     ap.add_argument("--no-fuse", action="store_true", help="run t0 as two HBM sweeps (Z pass, Y pass) instead of the fused kernel")
+    ap.add_argument("--overlap", action="store_true", help="EXPERIMENTAL: whole forward transform as one kernel, t3 overlapped behind per-part arrivals (P2P, N > 1)")
     ap.add_argument("--fuse", action="store_true", help="force the fused L2-resident t0 kernel (default: only with the P2P exchange)")
     args = ap.parse_args()
     if args.impl == "reference":

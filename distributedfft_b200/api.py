@@ -22,13 +22,14 @@ EXCHANGE_AUTO, EXCHANGE_P2P, EXCHANGE_NCCL, EXCHANGE_STAGED = 0, 1, 2, 3
 SCALE_BACKWARD = 4
 NO_FUSE = 8
 FORCE_FUSE = 16
+OVERLAP_X = 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfft.so")
 
 __all__ = [
     "FORWARD", "BACKWARD", "ALLOC_CPU", "ALLOC_DEV", "DOUBLE", "FLOAT", "EXCHANGE_AUTO", "EXCHANGE_P2P",
-    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
+    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "OVERLAP_X", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
     "fft_lines", "LinesPlan", "length_kind", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
@@ -254,6 +255,11 @@ class Plan:
     @property
     def fused(self):
         return bool(lib().dfft_plan_fused(self.handle))
+
+    @property
+    def overlapped(self):
+        """forward transform runs as the single overlapped kernel (OVERLAP_X, experimental)"""
+        return lib().dfft_plan_fused(self.handle) == 2
 
     @property
     def stream(self):

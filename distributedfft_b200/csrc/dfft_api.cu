@@ -315,6 +315,7 @@ static NcclApi& nccl_api()
 struct SyncBlock {
     unsigned long long arrive[DFFT_MAX_CHUNKS];  // arrive[s] = e : sender s finished writing my recv buffer for epoch e
     unsigned long long ready[DFFT_MAX_CHUNKS];   // ready[r] = e  : receiver r finished reading its recv buffer of epoch e
+    unsigned long long part_arrive[DFFT_MAX_PARTS][DFFT_MAX_CHUNKS];   // overlapped mode: part k of sender s has arrived (epoch e)
 };
 struct FlagPtrs {
     unsigned long long* p[DFFT_MAX_CHUNKS];
@@ -376,6 +377,12 @@ struct dfft_plan_s {
     unsigned long long* plane_done = nullptr;
     unsigned int* ticket = nullptr;
     unsigned long long fuse_epoch = 0;
+    // overlapped forward (fft_fused3_kernel): own intermediate buffer, per-part counters
+    bool overlap = false;
+    int parts = 1;
+    void* mid = nullptr;
+    unsigned long long* part_done = nullptr;
+    unsigned long long overlap_epoch = 0;
 };
 
 template <typename T> static void upload_lut(void** dst, int nstages, const int* rad)
@@ -523,6 +530,29 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     }
     p->xmode = xmode;
     if (xmode != DFFT_EXCHANGE_STAGED) CUP(cudaMalloc(&p->work, (size_t)p->max_count * p->esz));
+    {
+        // opt-in: the whole forward transform of a device as one kernel with t3 overlapped behind per-part arrivals
+        const char* env = getenv("DFFT_OVERLAP");
+        const bool want = (flags & DFFT_OVERLAP_X) || (env && strcmp(env, "0") != 0);
+        if (want && P > 1 && xmode == DFFT_EXCHANGE_P2P && direction == DFFT_FORWARD && p->fuse && ez->fused3 && ex == ez) {
+            const int cy = ez->p_C, cx_ = ez->x_C;
+            int lcm = cy > cx_ ? cy : cx_;   // both are powers of two in the tuned tables
+            if (lcm % cy == 0 && lcm % cx_ == 0) {
+                int K = 1;
+                for (int k : {4, 2})
+                    if (n2 % ((long long)k * lcm) == 0) { K = k; break; }
+                if (getenv("DFFT_PARTS")) {
+                    const int k = atoi(getenv("DFFT_PARTS"));
+                    if (k >= 1 && k <= DFFT_MAX_PARTS && n2 % ((long long)k * lcm) == 0) K = k;
+                }
+                p->parts = K;
+                p->overlap = true;
+                CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
+                CUP(cudaMalloc((void**)&p->part_done, DFFT_MAX_PARTS * sizeof(unsigned long long)));
+                CUP(cudaMemset(p->part_done, 0, DFFT_MAX_PARTS * sizeof(unsigned long long)));
+            }
+        }
+    }
     if (P > 1) {
         if (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_STAGED) {
             if (xmode == DFFT_EXCHANGE_P2P) {
@@ -570,6 +600,8 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->buf1) cudaFree(p->buf1);
     if (p->work) cudaFree(p->work);
     if (p->sync) cudaFree(p->sync);
+    if (p->mid) cudaFree(p->mid);
+    if (p->part_done) cudaFree(p->part_done);
     if (p->plane_done) cudaFree(p->plane_done);
     if (p->ticket) cudaFree(p->ticket);
     if (p->lut_z) cudaFree(p->lut_z);
@@ -673,6 +705,45 @@ template <typename T> struct Pass {
         cudaEventRecord(p->pev[1][0], p->stream);
         cudaEventRecord(p->pev[1][1], p->stream);
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "fused t0 launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
+    }
+    // forward t0 + t1 + t2 + t3 in one kernel (P2P, square planes): Z: buf1 -> mid, Y: mid -> peers' work, X: work -> buf2
+    static int fwd_overlapped(dfft_plan p, void* const* peer_base)
+    {
+        const Geom& g = p->g;
+        const SizeEntry* e = p->ez;
+        TileArgs<T> z{}, y{}, x{};
+        const int CZ = e->f_zCp, CY = e->p_C, CX = e->x_C;
+        z.lut = (const cx<T>*)p->lut_z; y.lut = (const cx<T>*)p->lut_y; x.lut = (const cx<T>*)p->lut_x;
+        z.G = (int)cdiv(g.n1, CZ); z.W = (int)g.n1; z.ntiles = p->n0l * z.G;
+        z.ia = Affine{g.n1 * g.n2, (long long)CZ * g.n2, g.n2, 1}; z.oa = z.ia;
+        z.in = (const cx<T>*)p->buf1; z.out = (cx<T>*)p->mid;
+        y.G = (int)cdiv(g.n2, CY); y.W = (int)g.n2; y.ntiles = p->n0l * y.G;
+        y.ia = Affine{g.n1 * g.n2, CY, 1, g.n2}; y.oa = y.ia;
+        y.in = (const cx<T>*)p->mid; y.out = nullptr;
+        y.co.ediv = (int)g.yd(); y.co.nchunks = p->P;
+        for (int q = 0; q < p->P; q++) { y.co.cptr[q] = peer_base[q]; y.co.SAq[q] = g.n1l(q) * g.n2; }
+        x.G = (int)cdiv(g.n2, CX); x.W = (int)g.n2; x.ntiles = p->n1l * x.G;
+        x.ia = Affine{g.n2, CX, 1, p->n1l * g.n2};
+        x.oa = Affine{g.n2 * g.n0, (long long)CX * g.n0, g.n0, 1};
+        x.in = (const cx<T>*)p->work; x.out = (cx<T>*)p->buf2;
+        Fused3Ctl c{};
+        c.plane_done = p->plane_done; c.ticket = p->ticket; c.part_done = p->part_done;
+        c.planes = p->n0l; c.rows = p->n1l; c.P = p->P; c.me = p->me;
+        c.K = p->parts;
+        c.GA = z.G; c.GB = y.G; c.GBk = y.G / c.K; c.GX = x.G; c.GXk = x.G / c.K;
+        c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
+        c.epoch = ++p->overlap_epoch;
+        c.part_target = c.epoch * (unsigned long long)(p->n0l * c.GBk);
+        c.my_arrive = &p->sync->part_arrive[0][0];
+        for (int q = 0; q < p->P; q++) c.peer_arrive[q] = &p->peer_sync[q]->part_arrive[0][0];
+        c.lag = p->lag;
+        cudaEventRecord(p->pev[0][0], p->stream);
+        cudaError_t err = e->fused3(&z, &y, &x, &c, p->sms, p->stream);
+        cudaEventRecord(p->pev[0][1], p->stream);
+        for (int a = 1; a < 3; a++) { cudaEventRecord(p->pev[a][0], p->stream); cudaEventRecord(p->pev[a][1], p->stream); }
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "overlapped forward launch (N=%d) failed: %s", e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
     }
@@ -802,6 +873,16 @@ template <typename T> static int execute_fused(dfft_plan p)
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
             p->epoch++;
+            if (p->overlap) {
+                if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
+                if ((rc = Pass<T>::fwd_overlapped(p, base))) return rc;
+                CU(cudaEventRecord(p->ev[1], p->stream));
+                CU(cudaEventRecord(p->ev[2], p->stream));
+                if ((rc = flags_signal(p, false, p->epoch))) return rc;
+                CU(cudaEventRecord(p->ev[3], p->stream));
+                p->timed = true;
+                return 0;
+            }
             if (p->fuse) {
                 if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
                 if ((rc = Pass<T>::zy_fused(p, p->buf1, p->buf2, nullptr, 1, base, false))) return rc;
@@ -1023,7 +1104,7 @@ extern "C" int dfft_plan_counts(dfft_plan p, long long* ic, long long* oc, long 
 }
 extern "C" int dfft_plan_launches(dfft_plan p) { return p ? p->launches : 0; }
 extern "C" int dfft_plan_exchange(dfft_plan p) { return p ? p->xmode : 0; }
-extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? 1 : 0; }
+extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? (p->overlap ? 2 : 1) : 0; }
 extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }
 
 // ------------------------------------------------------------------------------------------------

@@ -31,6 +31,8 @@ enum FusedKind {
     FK_COUNT
 };
 typedef cudaError_t (*FusedLaunchFn)(const void* args_a, const void* args_b, const FusedCtl* ctl, int sm_count, cudaStream_t stream);
+// forward t0..t3 of one device in one kernel (fft_fused3_kernel): Z, Y with peer stores, X behind per-part arrival flags
+typedef cudaError_t (*Fused3LaunchFn)(const void* args_z, const void* args_y, const void* args_x, const Fused3Ctl* ctl, int sm_count, cudaStream_t stream);
 
 struct SizeEntry {
     int N;
@@ -43,6 +45,7 @@ struct SizeEntry {
     PassLaunchFn launch[PK_COUNT];
     int f_zC, f_zCp;      // lines per contiguous tile inside the fused kernels (same CTA size as the strided role; p: peer-store kind)
     FusedLaunchFn fused[FK_COUNT];   // valid for square planes (N1 == N2 == N): both roles come from this entry
+    Fused3LaunchFn fused3;           // same restriction, and the X configuration must fill the same CTA as the peer-store Y role (else nullptr)
     const void* gen;      // run-time schedule (GenSched) of a generic-length entry, nullptr for tuned lengths
 };
 

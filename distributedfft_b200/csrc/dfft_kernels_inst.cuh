@@ -64,6 +64,39 @@ cudaError_t launch_fused(const void* va, const void* vb, const FusedCtl* ctl, in
     return cudaGetLastError();
 }
 
+template <class OpA, class OpB, class OpC, typename T, int MINB>
+cudaError_t launch_fused3(const void* va, const void* vb, const void* vc, const Fused3Ctl* ctl, int sm_count, cudaStream_t st)
+{
+    const TileArgs<T>& a = *reinterpret_cast<const TileArgs<T>*>(va);
+    const TileArgs<T>& b = *reinterpret_cast<const TileArgs<T>*>(vb);
+    const TileArgs<T>& c = *reinterpret_cast<const TileArgs<T>*>(vc);
+    auto kern = fft_fused3_kernel<OpA, OpB, OpC, T, MINB>;
+    constexpr size_t e1 = OpA::SM::exch_bytes > OpB::SM::exch_bytes ? OpA::SM::exch_bytes : OpB::SM::exch_bytes;
+    constexpr size_t exch = e1 > OpC::SM::exch_bytes ? e1 : OpC::SM::exch_bytes;
+    constexpr size_t smem = exch + OpA::aux_bytes + OpB::aux_bytes + OpC::aux_bytes;
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int occ = occ_cache[dev & 63].load();
+    if (occ == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OpA::NT, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        occ_cache[dev & 63].store(occ);
+    }
+    if (ctl->planes <= 0) return cudaSuccess;
+    const long long total = ctl->planes * ((long long)ctl->GA + ctl->GB) + ctl->rows * (long long)ctl->GX;
+    long long grid = (long long)sm_count * occ;
+    if (grid > total) grid = total;
+    Fused3Ctl f = *ctl;
+    if (f.lag <= 0) f.lag = (int)((grid + f.GA + f.GBk - 1) / ((long long)f.GA + f.GBk)) + 1;
+    kern<<<(unsigned)grid, OpA::NT, smem, st>>>(a, b, c, f);
+    return cudaGetLastError();
+}
+
 template <class S> void fill_rad(int& n, int* rad)
 {
     n = S::NSTAGES;
@@ -119,6 +152,11 @@ SizeEntry make_entry(int variant = 0)
     e.fused[FK_ZY_CO] = launch_fused<OZp, OYco, T, PEER::MB>;
     e.fused[FK_YZ] = launch_fused<OY, OZ, T, Y::MB>;
     e.fused[FK_YZ_CI] = launch_fused<OYci, OZ, T, Y::MB>;
+    // whole forward transform of a device in one kernel: needs the X role to fill the peer-store CTA shape
+    if constexpr (XS::T * X::C == NTP) {
+        using OX = TileOp<XS, T, X::C, MAP_C, MAP_T, false, false, false, false>;
+        e.fused3 = launch_fused3<OZp, OYco, OX, T, (PEER::MB < X::MB ? PEER::MB : X::MB)>;
+    } else e.fused3 = nullptr;
     return e;
 }
 

@@ -385,4 +385,154 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Forward t0 + t1 + t2 + t3 of one device in ONE persistent kernel (P2P exchange, square planes):
+// role A = Z tiles, role B = Y tiles whose chunked store lands in the peers' receive buffers over NVLink,
+// role C = X tiles reading this device's receive buffer.  The z axis is cut into K parts; the Y role sends
+// part 0 of every plane first (fused with the Z role through L2 as in fft_fused2_kernel), then parts 1..K-1;
+// as soon as part k has arrived from all P senders the X role can transform the (y_l, z in part k) lines, so
+// all but the last part of t3 runs while the NVLink-bound sends of later parts are still in flight.
+//   sender side : every finished Y tile of part k bumps part_done[k]; the tile that completes the part
+//                 publishes arrive[k][me] = epoch at every peer (fence.sys + st.release.sys)
+//   receiver    : an X tile of part k polls arrive[k][0..P) with ld.acquire.sys
+// Z and Y tiles never wait on a remote device, X tiles wait only on remote Y progress: no cross-device cycle;
+// inside the device the ticket order argument of fft_fused2_kernel applies unchanged.
+// ------------------------------------------------------------------------------------------
+constexpr int DFFT_MAX_PARTS = 8;
+
+struct Fused3Ctl {
+    unsigned long long* plane_done;     // [planes]  Z-role completion per plane (monotonic)
+    unsigned int* ticket;               // [0] next ticket, [1] CTAs that have left
+    unsigned long long* part_done;      // [K]       finished Y tiles per part (monotonic)
+    unsigned long long target;          // plane_done value meaning "Z finished this plane in this execute"
+    unsigned long long part_target;     // part_done value meaning "every Y tile of the part is stored"
+    unsigned long long epoch;           // value published in / awaited from the arrive flags
+    const unsigned long long* my_arrive;                   // [K][DFFT_MAX_CHUNKS] on this device
+    unsigned long long* peer_arrive[DFFT_MAX_CHUNKS];      // the same array on device q (peer mapped)
+    long long planes, rows;             // local x planes (n0_l), local y rows after the exchange (n1_l)
+    int P, me;
+    int GA, GB, GBk, GX, GXk, K;        // tiles per plane (Z, Y), Y tiles per plane and part, X tiles per row (all, per part), parts
+    int lag;
+};
+
+template <class OpA, class OpB, class OpC, typename T, int MINB>
+__global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArgs<T> A, const TileArgs<T> B, const TileArgs<T> Cc, const Fused3Ctl F)
+{
+    static_assert(OpA::NT == OpB::NT && OpB::NT == OpC::NT, "all roles use the whole CTA");
+    constexpr size_t e1 = OpA::SM::exch_bytes > OpB::SM::exch_bytes ? OpA::SM::exch_bytes : OpB::SM::exch_bytes;
+    constexpr size_t exch = e1 > OpC::SM::exch_bytes ? e1 : OpC::SM::exch_bytes;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_ticket;
+    typename OpA::Ctx ka;
+    typename OpB::Ctx kb;
+    typename OpC::Ctx kc;
+    OpA::setup(A, smem_raw, smem_raw + exch, ka);
+    OpB::setup(B, smem_raw, smem_raw + exch + OpA::aux_bytes, kb);
+    OpC::setup(Cc, smem_raw, smem_raw + exch + OpA::aux_bytes + OpB::aux_bytes, kc);
+    cx<T> twa[OpA::NTW], twb[OpB::NTW], twc[OpC::NTW];
+    OpA::load_twiddles(ka, twa);
+    OpB::load_twiddles(kb, twb);
+    OpC::load_twiddles(kc, twc);
+
+    const long long lag = F.lag < F.planes ? F.lag : F.planes;
+    // phase 0: Z on every plane + Y part 0, interleaved like fft_fused2_kernel
+    const long long headT = lag * F.GA;
+    const long long midT = (F.planes - lag) * ((long long)F.GA + F.GBk);
+    const long long L0 = headT + midT + lag * F.GBk;
+    // phases 1..K-1: Y part k (LY tiles) merged with X part k-1 (LX tiles); X starts after a quarter of the Y tiles
+    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
+    const long long dly = LY / 4, LM = LY - dly + LX;
+    const long long total = L0 + (long long)(F.K - 1) * (LY + LX) + LX;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(F.ticket, 1u);
+        __syncthreads();
+        const long long t = s_ticket;
+        if (t >= total) break;
+        int role;            // 0 = Z, 1 = Y, 2 = X
+        int part = 0;
+        long long plane = 0, idx = 0;   // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
+        if (t < L0) {
+            if (t < headT) { role = 0; plane = t / F.GA; idx = t - plane * F.GA; }
+            else if (t < headT + midT) {
+                const long long u = t - headT, i = u / (F.GA + F.GBk), r = u - i * (F.GA + F.GBk);
+                if (r < F.GA) { role = 0; plane = lag + i; idx = r; }
+                else { role = 1; plane = i; idx = r - F.GA; }
+            } else {
+                const long long u = t - headT - midT, i = u / F.GBk;
+                role = 1; plane = F.planes - lag + i; idx = u - i * F.GBk;
+            }
+        } else {
+            const long long u0 = t - L0;
+            const long long ph = u0 / (LY + LX);          // 0-based: phase ph+1, or K-1 for the final X part
+            const long long u = u0 - ph * (LY + LX);
+            if (ph >= F.K - 1) { role = 2; part = F.K - 1; idx = u; }
+            else {
+                long long yi;
+                bool isx = false;
+                if (u < dly) yi = u;
+                else {
+                    const long long v = u - dly;
+                    const long long xc0 = v * LX / LM, xc1 = (v + 1) * LX / LM;   // X tiles placed before position v / v+1
+                    if (xc1 > xc0) { isx = true; yi = xc0; }
+                    else yi = dly + v - xc0;
+                }
+                if (isx) { role = 2; part = (int)ph; idx = yi; }
+                else { role = 1; part = (int)ph + 1; plane = yi / F.GBk; idx = yi - plane * F.GBk; }
+            }
+        }
+        if (role == 0) {
+            OpA::run(A, ka, plane * F.GA + idx, twa);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(F.plane_done + plane, 1ull);
+            }
+        } else if (role == 1) {
+            if (threadIdx.x == 0) {
+                unsigned long long v;
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(F.plane_done + plane) : "memory");
+                    if (v >= F.target) break;
+                    __nanosleep(64);
+                    if (++spins > (1u << 25)) __trap();
+                }
+            }
+            __syncthreads();
+            OpB::run(B, kb, plane * F.GB + (long long)part * F.GBk + idx, twb);
+            __syncthreads();                                   // every thread's peer stores are issued
+            if (threadIdx.x == 0) {
+                __threadfence_system();                        // ... and ordered (system scope) before the count
+                const unsigned long long old = atomicAdd(F.part_done + part, 1ull);
+                if (old + 1 == F.part_target) {                // this tile completes the part on this device
+                    __threadfence_system();
+                    for (int q = 0; q < F.P; q++)
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.peer_arrive[q] + (size_t)part * DFFT_MAX_CHUNKS + F.me), "l"(F.epoch) : "memory");
+                }
+            }
+        } else {
+            if (threadIdx.x < F.P) {
+                const unsigned long long* flag = F.my_arrive + (size_t)part * DFFT_MAX_CHUNKS + threadIdx.x;
+                unsigned long long v;
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+                    if (v >= F.epoch) break;
+                    __nanosleep(128);
+                    if (++spins > (1u << 25)) __trap();
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            const long long row = idx / F.GXk, bb = idx - row * F.GXk;
+            OpC::run(Cc, kc, row * F.GX + (long long)part * F.GXk + bb, twc);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const unsigned left = atomicAdd(F.ticket + 1, 1u);
+        if (left == gridDim.x - 1) { F.ticket[0] = 0; F.ticket[1] = 0; __threadfence(); }
+    }
+}
+
 }  // namespace dfft

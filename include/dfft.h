@@ -52,6 +52,10 @@ extern "C" {
                                     Default: fused when the exchange is P2P (the Y stores are NVLink-bound and hide the
                                     Z role), two sweeps otherwise */
 
+#define DFFT_OVERLAP_X 32u       /* EXPERIMENTAL (forward, P2P, square planes): the whole transform of a device as one kernel;
+                                    the z axis is sent in parts and the X lines of a part start as soon as it has arrived
+                                    from every sender, overlapping t3 with the NVLink-bound sends (env DFFT_OVERLAP=1) */
+
 #define DFFT_EINVAL (-1)
 #define DFFT_ECUDA (-2)
 #define DFFT_EUNSUPPORTED (-3)
@@ -143,7 +147,8 @@ int dfft_plan_buffers(dfft_plan plan, void** buffer1, void** buffer2);
 int dfft_plan_counts(dfft_plan plan, long long* in_count, long long* out_count, long long* max_count);
 /* kernels launched by the last execute (for bench.py's gpu_launches) */
 int dfft_plan_launches(dfft_plan plan);
-/* 1 when t0 runs as the fused two-pass kernel (square planes, N1 == N2), else 0 */
+/* 2: forward transform runs as the single overlapped kernel (DFFT_OVERLAP_X); 1: t0 runs as the fused two-pass
+ * kernel (square planes, N1 == N2); 0: separate passes */
 int dfft_plan_fused(dfft_plan plan);
 /* which exchange the plan resolved to (DFFT_EXCHANGE_*) */
 int dfft_plan_exchange(dfft_plan plan);

@@ -204,3 +204,23 @@ def test_process_per_gpu_bootstrap(tmp_path, mode):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for k in range(P):
         assert f"rank {k} ok" in r.stdout
+
+
+EXPERIMENTAL = os.environ.get("DFFT_TEST_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental overlapped forward kernel: set DFFT_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("P,n", [(2, 64), (4, 64), (8, 64), (2, 128), (2, 256), (8, 256)])
+def test_overlapped_forward_matches_default_path(P, n):
+    """DFFT_OVERLAP_X (fft_fused3_kernel: Z + Y/peer-store + X roles, per-part arrival flags) must produce the same
+    y-slabs as the default P2P path, bit for bit, over repeated executes."""
+    need(P)
+    n0 = n   # the single-kernel path needs a cube (all three axes share one table entry)
+    ns = NumpySlab(n0, n, n, P)
+    rng = np.random.default_rng(n + P)
+    A = rng.standard_normal((n0, n, n)) + 1j * rng.standard_normal((n0, n, n))
+    a = run_slab(n0, n, n, P, FORWARD, ns.scatter_input(A), flags=dfft.EXCHANGE_P2P, repeat=3, refill=False)
+    b = run_slab(n0, n, n, P, FORWARD, ns.scatter_input(A), flags=dfft.EXCHANGE_P2P | dfft.OVERLAP_X, repeat=3, refill=False)
+    for p in range(P):
+        assert b[p]["launches"] < a[p]["launches"]
+        assert np.array_equal(a[p]["buf2"], b[p]["buf2"]), p
