@@ -473,27 +473,6 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         upload_lut<float>(&p->lut_x, ex->x_nstages, ex->x_rad);
     }
     CUP(cudaGetLastError());
-    // the fused kernels pair the contiguous and the strided role of one table entry: square planes only
-    {
-        // policy: the fused kernel wins when the strided role's stores are NVLink-bound (P2P exchange: the
-        // contiguous role then hides entirely under the link time); on one GPU / NCCL the two HBM-bound sweeps
-        // are currently faster (profiles/: SM-side time of both roles adds up), so it is opt-in there.
-        const char* env = getenv("DFFT_FUSE");
-        const bool can = n1 == n2 && ez->fused[FK_ZY] != nullptr;
-        bool want = P > 1 && (flags & DFFT_EXCHANGE_MASK) != DFFT_EXCHANGE_NCCL && (flags & DFFT_EXCHANGE_MASK) != DFFT_EXCHANGE_STAGED;
-        if (env) want = strcmp(env, "0") != 0;
-        if (flags & DFFT_FORCE_FUSE) want = true;
-        if (flags & DFFT_NO_FUSE) want = false;
-        p->fuse = can && want;
-        if (getenv("DFFT_LAG")) p->lag = atoi(getenv("DFFT_LAG"));
-        if (p->fuse) {
-            CUP(cudaMalloc((void**)&p->plane_done, (size_t)p->n0l * sizeof(unsigned long long)));
-            CUP(cudaMemset(p->plane_done, 0, (size_t)p->n0l * sizeof(unsigned long long)));
-            CUP(cudaMalloc((void**)&p->ticket, 2 * sizeof(unsigned int)));
-            CUP(cudaMemset(p->ticket, 0, 2 * sizeof(unsigned int)));
-        }
-    }
-
     // exchange mode
     int xmode = (int)(flags & DFFT_EXCHANGE_MASK);
     if (P == 1) xmode = xmode == DFFT_EXCHANGE_STAGED ? DFFT_EXCHANGE_STAGED : DFFT_EXCHANGE_P2P;
@@ -529,6 +508,27 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         }
     }
     p->xmode = xmode;
+    // the fused kernels pair the contiguous and the strided role of one table entry: square planes only
+    {
+        // policy: the fused kernel wins when the strided role's stores are NVLink-bound (P2P exchange: the
+        // contiguous role then hides entirely under the link time); on one GPU / NCCL the two HBM-bound sweeps
+        // are currently faster (profiles/: SM-side time of both roles adds up), so it is opt-in there.
+        const char* env = getenv("DFFT_FUSE");
+        const bool can = n1 == n2 && ez->fused[FK_ZY] != nullptr;
+        bool want = P > 1 && xmode == DFFT_EXCHANGE_P2P;
+        if (env) want = strcmp(env, "0") != 0;
+        if (flags & DFFT_FORCE_FUSE) want = true;
+        if (flags & DFFT_NO_FUSE) want = false;
+        p->fuse = can && want;
+        if (getenv("DFFT_LAG")) p->lag = atoi(getenv("DFFT_LAG"));
+        if (p->fuse) {
+            CUP(cudaMalloc((void**)&p->plane_done, (size_t)p->n0l * sizeof(unsigned long long)));
+            CUP(cudaMemset(p->plane_done, 0, (size_t)p->n0l * sizeof(unsigned long long)));
+            CUP(cudaMalloc((void**)&p->ticket, 2 * sizeof(unsigned int)));
+            CUP(cudaMemset(p->ticket, 0, 2 * sizeof(unsigned int)));
+        }
+    }
+
     if (xmode != DFFT_EXCHANGE_STAGED) CUP(cudaMalloc(&p->work, (size_t)p->max_count * p->esz));
     {
         // opt-in: the whole forward transform of a device as one kernel with t3 overlapped behind per-part arrivals
