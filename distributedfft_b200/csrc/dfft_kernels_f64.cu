@@ -24,6 +24,12 @@ void register_f64(std::vector<SizeEntry>& v)
     // (finer-grained phases; the fused kernel's top stall is the CTA barrier, profiles/r1_ncu_full_fused_t0_512.txt)
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Cfg<Sched<512, 8, 8, 8, 8>, 4, false, 3, false>>(1));
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Cfg<Sched<512, 8, 8, 8, 8>, 2, false, 5, false>>(2));
+    // DFFT_VARIANT=3|4: the default / the 3-CTA shapes with L2 eviction hints in the fused kernels (streamed data evict_first,
+    // the Z->Y intermediate evict_last: the lag sweep says the intermediate survives only a few planes otherwise)
+    using Y512 = Cfg<Sched<512, 16, 8, 8, 8>, 8, false, 2, false>;
+    using Y512n = Cfg<Sched<512, 8, 8, 8, 8>, 4, false, 3, false>;
+    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512, Y512, Y512, 1>(3));
+    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512n, Y512n, Y512n, 1>(4));
     // mixed radix
     // 768 (kbench5): 24 points/thread (8.8.4.3, three exchanges instead of four): Z 2.83 vs 3.45 ms, Y 3.87 vs 4.28, X 3.52 vs 4.19
     v.push_back(make_entry<T, Cfg<Sched<768, 24, 8, 8, 4, 3>, 4, false, 2, false>, Cfg<Sched<768, 24, 8, 8, 4, 3>, 4, false, 2, false>>());

@@ -113,7 +113,9 @@ template <class S_, int C_, bool TW_, int MB_, bool PP_> struct Cfg {
 // Z: contiguous pass.  Y: strided pass on local memory (t0 axis-1, backward unpack).  X: the t3 passes (strided on one
 // side, contiguous on the other).  PEER: the Y pass with the chunked store (pack / peer receive buffers over NVLink),
 // which wants >= 128-byte row segments; must use Y's schedule (it shares the twiddle table).
-template <typename T, class Z, class Y, class X = Y, class PEER = Y>
+// FH = 1: the fused t0 kernels carry L2 eviction hints (first role: streamed input evict_first, intermediate evict_last;
+// second role: intermediate and output evict_first) -- an experiment, see DESIGN.md
+template <typename T, class Z, class Y, class X = Y, class PEER = Y, int FH = 0>
 SizeEntry make_entry(int variant = 0)
 {
     using ZS = typename Z::S;
@@ -143,15 +145,19 @@ SizeEntry make_entry(int variant = 0)
     static_assert(NT % ZS::T == 0 && NTP % ZS::T == 0, "strided CTA size must be a multiple of the contiguous line's thread count");
     e.f_zC = NT / ZS::T;
     e.f_zCp = NTP / ZS::T;
-    using OZ = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false>;
-    using OZp = TileOp<ZS, T, NTP / ZS::T, MAP_T, MAP_T, false, false, false, false>;
-    using OY = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, false, false, false>;
-    using OYco = TileOp<SS, T, PEER::C, MAP_C, MAP_C, false, false, true, false>;
-    using OYci = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, true, false, false>;
-    e.fused[FK_ZY] = launch_fused<OZ, OY, T, Y::MB>;
+    constexpr int H1 = FH ? 1 : 0, H2 = FH ? 2 : 0;
+    // first-role flavour (intermediate written with evict_last) and second-role flavour (everything evict_first)
+    using OZ = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H2>;
+    using OZ2 = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H1>;
+    using OZp = TileOp<ZS, T, NTP / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H2>;
+    using OY = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, false, false, false, false, H1, H2>;
+    using OY2 = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, false, false, false, false, H1, H1>;
+    using OYco = TileOp<SS, T, PEER::C, MAP_C, MAP_C, false, false, true, false, false, H1, 0>;
+    using OYci = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, true, false, false, false, H1, H2>;
+    e.fused[FK_ZY] = launch_fused<OZ, OY2, T, Y::MB>;
     e.fused[FK_ZY_CO] = launch_fused<OZp, OYco, T, PEER::MB>;
-    e.fused[FK_YZ] = launch_fused<OY, OZ, T, Y::MB>;
-    e.fused[FK_YZ_CI] = launch_fused<OYci, OZ, T, Y::MB>;
+    e.fused[FK_YZ] = launch_fused<OY, OZ2, T, Y::MB>;
+    e.fused[FK_YZ_CI] = launch_fused<OYci, OZ2, T, Y::MB>;
     // whole forward transform of a device in one kernel: needs the X role to fill the peer-store CTA shape
     if constexpr (XS::T * X::C == NTP) {
         using OX = TileOp<XS, T, X::C, MAP_C, MAP_T, false, false, false, false>;

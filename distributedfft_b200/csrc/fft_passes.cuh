@@ -101,6 +101,46 @@ template <int MAP, int C, int TT> __device__ __forceinline__ void thread_map(int
 template <typename C_> __device__ __forceinline__ C_ ld_stream(const C_* p) { return __ldcg(p); }
 template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { __stcg(p, v); }
 
+// L2 eviction-priority hints (createpolicy + .L2::cache_hint): 1 = evict_first (streamed once), 2 = evict_last (the
+// intermediate of the fused kernels, which must survive in L2 until the second role has read it)
+template <int H> __device__ __forceinline__ unsigned long long l2_policy()
+{
+    unsigned long long p = 0;
+    if constexpr (H == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    if constexpr (H == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double2 ld_hint(const double2* p, unsigned long long pol)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ld_hint(const float2* p, unsigned long long pol)
+{
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint(double2* p, double2 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float2* p, float2 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+template <int H, typename C_> __device__ __forceinline__ C_ ld_pol(const C_* p, unsigned long long pol)
+{
+    if constexpr (H == 0) return ld_stream(p);
+    else return ld_hint(p, pol);
+}
+template <int H, typename C_> __device__ __forceinline__ void st_pol(C_* p, C_ v, unsigned long long pol)
+{
+    if constexpr (H == 0) st_stream(p, v);
+    else st_hint(p, v, pol);
+}
+
 // per-thread asynchronous global -> shared copies (LDGSTS): the next tile's elements are fetched into the
 // thread's private staging slots while the current tile is being transformed
 template <int BYTES> __device__ __forceinline__ void cp_async(void* dst_smem, const void* src)
@@ -121,7 +161,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Shared-memory carve-up of one TileOp (offsets from its base):
 //   [0, exch_bytes) exchange buffer | lut_bytes twiddles | 16 B mbarrier | tab_bytes chunk tables
 // ------------------------------------------------------------------------------------------
-template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG, bool PF = false>
+template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG, bool PF = false,
+          int HIN = 0, int HOUT = 0>
 struct TileOp {
     using SM = TileSmem<S, T, C, PINGPONG>;
     static constexpr int R = S::R, TT = S::T, NT = S::T * C;
@@ -141,6 +182,7 @@ struct TileOp {
         int t_in, c_in, t_out, c_out;
         int pp;
         cx<T>* stage;
+        unsigned long long pol_in, pol_out;   // L2 cache policies (HIN / HOUT)
     };
 
     // exch: exchange buffer (SM::exch_bytes, may be shared with another TileOp); aux: aux_bytes of this op's own
@@ -158,6 +200,8 @@ struct TileOp {
         k.saq_i = reinterpret_cast<long long*>(k.cptr_o + DFFT_MAX_CHUNKS);
         k.saq_o = k.saq_i + DFFT_MAX_CHUNKS;
         k.pp = 0;
+        k.pol_in = l2_policy<HIN>();
+        k.pol_out = l2_policy<HOUT>();
         k.stage = reinterpret_cast<cx<T>*>(aux + SM::lut_bytes + 16 + (CHUNKED ? SM::tab_bytes : 0));
         thread_map<MAPIN, C, TT>(tid, k.t_in, k.c_in);
         thread_map<MAPOUT, C, TT>(tid, k.t_out, k.c_out);
@@ -234,14 +278,14 @@ struct TileOp {
             if constexpr (!CHUNK_IN) {
                 const cx<T>* p = A.in + a * A.ia.SA + b * A.ia.SB + c_in * A.ia.cs + (long long)t_in * A.ia.es;
 #pragma unroll
-                for (int u = 0; u < R; u++) v[u] = ok ? ld_stream(p + (long long)u * TT * A.ia.es) : mk<T>(0, 0);
+                for (int u = 0; u < R; u++) v[u] = ok ? ld_pol<HIN>(p + (long long)u * TT * A.ia.es, k.pol_in) : mk<T>(0, 0);
             } else {
                 const long long off = b * A.ia.SB + c_in * A.ia.cs;
 #pragma unroll
                 for (int u = 0; u < R; u++) {
                     const int2 qe = k.etab_i[t_in + u * TT];
                     const cx<T>* p = reinterpret_cast<const cx<T>*>(k.cptr_i[qe.x]) + a * k.saq_i[qe.x] + off + (long long)qe.y * A.ia.es;
-                    v[u] = ok ? ld_stream(p) : mk<T>(0, 0);
+                    v[u] = ok ? ld_pol<HIN>(p, k.pol_in) : mk<T>(0, 0);
                 }
             }
             if (inv) {
@@ -266,14 +310,14 @@ struct TileOp {
                 if constexpr (!CHUNK_OUT) {
                     cx<T>* p = A.out + a * A.oa.SA + b * A.oa.SB + c_out * A.oa.cs + (long long)t_out * A.oa.es;
 #pragma unroll
-                    for (int u = 0; u < R; u++) st_stream(p + (long long)u * TT * A.oa.es, v[u]);
+                    for (int u = 0; u < R; u++) st_pol<HOUT>(p + (long long)u * TT * A.oa.es, v[u], k.pol_out);
                 } else {
                     const long long off = b * A.oa.SB + c_out * A.oa.cs;
 #pragma unroll
                     for (int u = 0; u < R; u++) {
                         const int2 qe = k.etab_o[t_out + u * TT];
                         cx<T>* p = reinterpret_cast<cx<T>*>(k.cptr_o[qe.x]) + a * k.saq_o[qe.x] + off + (long long)qe.y * A.oa.es;
-                        st_stream(p, v[u]);
+                        st_pol<HOUT>(p, v[u], k.pol_out);
                     }
                 }
             }
