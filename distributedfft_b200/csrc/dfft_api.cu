@@ -1115,12 +1115,16 @@ struct LinePass {
     const SizeEntry* e = nullptr;
     int kind = PK_Z;
     void* lut = nullptr;
-    Affine ia{};
+    Affine ia{}, oa{};
     int G = 0, W = 0;
     long long ntiles = 0;
+    long long tw_n = 0;          // four-step twiddle modulus (PK_XF_TW)
+    int src = 0, dst = 0;        // 0 = the caller's data, 1 = the plan's temporary
 };
 struct dfft_lines_plan_s {
     int prec = 0, device = 0, sms = 148, npass = 0;
+    bool ordered = false;        // passes run in the same order for both directions (four-step)
+    void* temp = nullptr;
     LinePass pass[2];
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -1144,12 +1148,14 @@ static int make_line_pass(LinePass& lp, int n, long long stride, long long nline
         const int C = e->z_C;
         lp.G = (int)cdiv(nlines, C); lp.W = (int)std::min<long long>(nlines, 0x7fffffff); lp.ntiles = lp.G;
         lp.ia = Affine{0, (long long)C * n, n, 1};
+        lp.oa = lp.ia;
         lp.kind = PK_Z;
     } else {
         if (inner_dist != 1 || inner < 1 || nlines % inner) return fail(DFFT_EUNSUPPORTED, "strided lines must be columns (inner_dist == 1)");
         const int C = e->s_C;
         lp.G = (int)cdiv(inner, C); lp.W = (int)inner; lp.ntiles = (nlines / inner) * lp.G;
         lp.ia = Affine{outer_dist, C, 1, stride};
+        lp.oa = lp.ia;
         lp.kind = PK_Y;
     }
     if (precision == DFFT_DOUBLE) upload_lut_e<double>(&lp.lut, e, stride == 1);
@@ -1174,10 +1180,63 @@ extern "C" int dfft_lines_destroy(dfft_lines_plan p)
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (int i = 0; i < 2; i++) if (p->pass[i].lut) cudaFree(p->pass[i].lut);
+    if (p->temp) cudaFree(p->temp);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaGetLastError();
     delete p;
+    return 0;
+}
+
+// Long contiguous lines (beyond one shared-memory line): four-step decomposition n = n1 * n2 in two passes,
+//   A: view the line as [n1][n2]; FFT along n1 (stride n2), multiply by W_n^(n2*k1), store transposed -> temp [n2][k1]
+//   B: FFT along n2 (stride n1) of temp, stored to the caller's buffer at [k2][k1] = natural order X[k1 + n1*k2]
+// -- what the reference does with its multi-upload axes and reorderFourStep = 1 (templateFFT.cpp:4007-4106, 5951).
+// EXPERIMENTAL until it has been run against the oracle on hardware: enabled with DFFT_EXPERIMENTAL_LONG=1.
+static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precision)
+{
+    long long best1 = 0;
+    int best_score = -1;
+    for (long long d = 2; d * d <= (long long)n * 4 && d < n; d++) {
+        if (n % d) continue;
+        const SizeEntry *e1 = find_size_entry((int)d, precision), *e2 = find_size_entry((int)(n / d), precision);
+        if (!e1 || !e2) continue;
+        const long long q = n / d;
+        const double ratio = d > q ? (double)d / q : (double)q / d;
+        int score = (e1->gen ? 0 : 1000) + (e2->gen ? 0 : 1000) + (int)(500.0 / ratio);
+        if (score > best_score) { best_score = score; best1 = d; }
+    }
+    if (!best1) return fail(DFFT_EUNSUPPORTED, "length %d cannot be split into two supported factors", n);
+    const int n1 = (int)best1, n2 = n / n1;
+    const size_t esz = precision == DFFT_FLOAT ? 8 : 16;
+    CU(cudaMalloc(&p->temp, (size_t)nlines * n * esz));
+    // pass A: columns of the [n1][n2] matrix of every line, transposed store + twiddle
+    LinePass& a = p->pass[0];
+    a.e = find_size_entry(n1, precision);
+    {
+        const int C = a.e->x_C;
+        a.G = (int)cdiv(n2, C); a.W = n2; a.ntiles = nlines * a.G;
+        a.ia = Affine{(long long)n, C, 1, n2};
+        a.oa = Affine{(long long)n, (long long)C * n1, n1, 1};
+        a.kind = PK_XF_TW; a.tw_n = n; a.src = 0; a.dst = 1;
+        if (precision == DFFT_DOUBLE) upload_lut<double>(&a.lut, a.e->x_nstages, a.e->x_rad);
+        else upload_lut<float>(&a.lut, a.e->x_nstages, a.e->x_rad);
+    }
+    // pass B: columns of the [n2][n1] matrix in temp, natural-order result in the caller's buffer
+    LinePass& b = p->pass[1];
+    b.e = find_size_entry(n2, precision);
+    {
+        const int C = b.e->s_C;
+        b.G = (int)cdiv(n1, C); b.W = n1; b.ntiles = nlines * b.G;
+        b.ia = Affine{(long long)n, C, 1, n1};
+        b.oa = b.ia;
+        b.kind = PK_Y; b.src = 1; b.dst = 0;
+        if (precision == DFFT_DOUBLE) upload_lut<double>(&b.lut, b.e->s_nstages, b.e->s_rad);
+        else upload_lut<float>(&b.lut, b.e->s_nstages, b.e->s_rad);
+    }
+    if (cudaGetLastError() != cudaSuccess || !a.lut || !b.lut) return fail(DFFT_ECUDA, "twiddle table upload failed");
+    p->npass = 2;
+    p->ordered = true;
     return 0;
 }
 
@@ -1189,9 +1248,14 @@ extern "C" int dfft_lines_plan_create(int n, long long stride, long long nlines,
     if (n < 1 || nlines < 0 || stride < 1 || (precision != DFFT_DOUBLE && precision != DFFT_FLOAT)) return fail(DFFT_EINVAL, "bad arguments");
     dfft_lines_plan p = new dfft_lines_plan_s;
     int rc = lines_plan_common(p, precision);
-    if (!rc) rc = make_line_pass(p->pass[0], n, stride, nlines, inner, inner_dist, outer_dist, precision);
+    const char* lng = getenv("DFFT_EXPERIMENTAL_LONG");
+    if (!rc && !find_size_entry(n, precision) && stride == 1 && inner_dist == n && lng && atoi(lng) != 0) {
+        rc = make_four_step(p, n, nlines, precision);
+    } else {
+        if (!rc) rc = make_line_pass(p->pass[0], n, stride, nlines, inner, inner_dist, outer_dist, precision);
+        p->npass = 1;
+    }
     if (rc) { dfft_lines_destroy(p); return rc; }
-    p->npass = 1;
     *out = p;
     return 0;
 }
@@ -1216,12 +1280,12 @@ template <typename T> static int lines_execute_impl(dfft_lines_plan p, void* dat
 {
     CU(cudaEventRecord(p->ev[0], p->stream));
     for (int k = 0; k < p->npass; k++) {
-        const LinePass& lp = p->pass[direction == DFFT_BACKWARD ? p->npass - 1 - k : k];
+        const LinePass& lp = p->pass[(direction == DFFT_BACKWARD && !p->ordered) ? p->npass - 1 - k : k];
         if (lp.ntiles <= 0) continue;
         TileArgs<T> a{};
-        a.in = (const cx<T>*)data; a.out = (cx<T>*)data; a.lut = (const cx<T>*)lp.lut;
-        a.ia = lp.ia; a.oa = lp.ia; a.G = lp.G; a.W = lp.W; a.ntiles = lp.ntiles;
-        a.inv = direction == DFFT_BACKWARD; a.gen = lp.e->gen;
+        a.in = (const cx<T>*)(lp.src ? p->temp : data); a.out = (cx<T>*)(lp.dst ? p->temp : data); a.lut = (const cx<T>*)lp.lut;
+        a.ia = lp.ia; a.oa = lp.oa; a.G = lp.G; a.W = lp.W; a.ntiles = lp.ntiles;
+        a.inv = direction == DFFT_BACKWARD; a.gen = lp.e->gen; a.tw_n = lp.tw_n;
         cudaError_t err = lp.e->launch[lp.kind](&a, p->sms, p->stream);
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "line pass launch failed: %s", cudaGetErrorString(err));
     }

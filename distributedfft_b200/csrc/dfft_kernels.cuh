@@ -17,6 +17,7 @@ enum PassKind {
     PK_XF,         // strided load, transposed contiguous store (MAP_C -> MAP_T)
     PK_XB,         // contiguous load, strided store (MAP_T -> MAP_C)
     PK_XB_CO,      // + chunked (peer) store
+    PK_XF_TW,      // PK_XF + four-step twiddle epilogue (first pass of a long 1-D transform)
     PK_COUNT
 };
 

@@ -82,6 +82,7 @@ template <typename T> static void fill_launchers(SizeEntry& e)
     e.launch[PK_XF] = launch_generic<T, MAP_C, MAP_T, false, false>;
     e.launch[PK_XB] = launch_generic<T, MAP_T, MAP_C, false, false>;
     e.launch[PK_XB_CO] = launch_generic<T, MAP_T, MAP_C, false, true>;
+    e.launch[PK_XF_TW] = launch_generic<T, MAP_C, MAP_T, false, false>;   // the twiddle epilogue is a run-time switch (TileArgs::tw_n)
 }
 
 const SizeEntry* generic_size_entry(int N, int prec)

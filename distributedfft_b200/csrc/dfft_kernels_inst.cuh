@@ -7,11 +7,11 @@
 
 namespace dfft {
 
-template <class S, typename T, int C, int MI, int MO, bool TW, bool CI, bool CO, int MINB, bool PP>
+template <class S, typename T, int C, int MI, int MO, bool TW, bool CI, bool CO, int MINB, bool PP, bool EPI = false>
 cudaError_t launch_pass(const void* vargs, int sm_count, cudaStream_t st)
 {
     const TileArgs<T>& a = *reinterpret_cast<const TileArgs<T>*>(vargs);
-    auto kern = fft_tile_kernel<S, T, C, MI, MO, TW, CI, CO, MINB, PP>;
+    auto kern = fft_tile_kernel<S, T, C, MI, MO, TW, CI, CO, MINB, PP, false, EPI>;
     constexpr size_t smem = TileSmem<S, T, C, PP>::bytes(CI || CO);
     static std::atomic<int> occ_cache[64];
     int dev = 0;
@@ -140,6 +140,7 @@ SizeEntry make_entry(int variant = 0)
     e.launch[PK_XF] = launch_pass<XS, T, X::C, MAP_C, MAP_T, X::TW, false, false, X::MB, X::PP>;
     e.launch[PK_XB] = launch_pass<XS, T, X::C, MAP_T, MAP_C, X::TW, false, false, X::MB, X::PP>;
     e.launch[PK_XB_CO] = launch_pass<XS, T, X::C, MAP_T, MAP_C, X::TW, false, true, X::MB, X::PP>;
+    e.launch[PK_XF_TW] = launch_pass<XS, T, X::C, MAP_C, MAP_T, X::TW, false, false, X::MB, X::PP, true>;
     // fused two-pass kernels: the contiguous role is re-tiled so that both roles fill the same CTA
     constexpr int NT = SS::T * Y::C, NTP = SS::T * PEER::C;
     static_assert(NT % ZS::T == 0 && NTP % ZS::T == 0, "strided CTA size must be a multiple of the contiguous line's thread count");

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fft_generic_kernel(const TileArgs
             if (MAPOUT == MAP_T) { e = i % N; c = i / N; } else { c = i % C; e = i / C; }
             if (c >= valid) continue;
             cx<T> v = src[c * N + e];
+            if (A.tw_n) v = cmul(v, unit_root<T>((((long long)b * C + c) * (long long)e) % A.tw_n, A.tw_n));   // four-step twiddle
             if (inv) v = cswap(v);
             if (A.do_scale) { v.x *= A.scale; v.y *= A.scale; }
             cx<T>* p;

@@ -43,6 +43,7 @@ template <typename T> struct TileArgs {
     int do_scale;
     ChunkTab ci, co;       // used when CHUNK_IN / CHUNK_OUT
     const void* gen;       // host pointer to the GenSched of a generic-length entry (read by its launcher only)
+    long long tw_n;        // four-step epilogue (EPI): multiply output (column col, point k) by e^{-2 pi i col*k / tw_n}; 0 = off
 };
 
 template <class S, typename T, int C, bool PINGPONG>
@@ -100,6 +101,14 @@ template <int MAP, int C, int TT> __device__ __forceinline__ void thread_map(int
 // streaming accesses: every element is touched exactly once per pass, so keep it out of L1
 template <typename C_> __device__ __forceinline__ C_ ld_stream(const C_* p) { return __ldcg(p); }
 template <typename C_> __device__ __forceinline__ void st_stream(C_* p, C_ v) { __stcg(p, v); }
+
+// e^{-2 pi i m/n} evaluated on the fly (four-step twiddle between the two passes of a long 1-D transform)
+template <typename T> __device__ __forceinline__ cx<T> unit_root(long long m, long long n)
+{
+    double sn, cs;
+    sincospi(-2.0 * (double)m / (double)n, &sn, &cs);
+    return mk<T>((T)cs, (T)sn);
+}
 
 // L2 eviction-priority hints (createpolicy + .L2::cache_hint): 1 = evict_first (streamed once), 2 = evict_last (the
 // intermediate of the fused kernels, which must survive in L2 until the second role has read it)
@@ -162,7 +171,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   [0, exch_bytes) exchange buffer | lut_bytes twiddles | 16 B mbarrier | tab_bytes chunk tables
 // ------------------------------------------------------------------------------------------
 template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG, bool PF = false,
-          int HIN = 0, int HOUT = 0>
+          int HIN = 0, int HOUT = 0, bool EPI = false>
 struct TileOp {
     using SM = TileSmem<S, T, C, PINGPONG>;
     static constexpr int R = S::R, TT = S::T, NT = S::T * C;
@@ -296,6 +305,11 @@ struct TileOp {
         // the staging slots are free once the first stage has consumed the registers loaded from them
         auto hook = [&]() { if constexpr (PF) { if (next_tile >= 0) prefetch(A, k, next_tile); } };
         StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, k.exch, k.pp, k.lut_s, twr, hook);
+        if constexpr (EPI) {   // four-step twiddle W_n^(col * k), applied in the forward domain (before the inverse's swap-back)
+            const long long col = (long long)b * C + c_out;
+#pragma unroll
+            for (int u = 0; u < R; u++) v[u] = cmul(v[u], unit_root<T>((col * (long long)(t_out + u * TT)) % A.tw_n, A.tw_n));
+        }
         {
             if (inv) {
 #pragma unroll
@@ -326,12 +340,12 @@ struct TileOp {
 };
 
 template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, int MINB,
-          bool PINGPONG, bool PF = false>
+          bool PINGPONG, bool PF = false, bool EPI = false>
 __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<T> A)
 {
     static_assert(S::valid(), "bad schedule");
     static_assert(S::NSTAGES > 1 || MAPIN == MAPOUT, "a thread-map change needs an exchange");
-    using Op = TileOp<S, T, C, MAPIN, MAPOUT, TWREG, CHUNK_IN, CHUNK_OUT, PINGPONG, PF>;
+    using Op = TileOp<S, T, C, MAPIN, MAPOUT, TWREG, CHUNK_IN, CHUNK_OUT, PINGPONG, PF, 0, 0, EPI>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename Op::Ctx k;
     Op::setup(A, smem_raw, smem_raw + Op::SM::exch_bytes, k);

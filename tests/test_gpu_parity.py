@@ -377,3 +377,23 @@ def test_compute_sanitizer_memcheck_and_racecheck():
         r = subprocess.run([cs, "--tool", tool, "--error-exitcode", "7", exe, "16", "16", "16", "1"], capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (tool, r.stdout[-3000:], r.stderr[-2000:])
         assert "ERROR SUMMARY: 0 errors" in r.stdout or "RACECHECK SUMMARY: 0 hazards" in r.stdout, (tool, r.stdout[-1500:])
+
+
+@pytest.mark.skipif(os.environ.get("DFFT_TEST_EXPERIMENTAL") != "1", reason="experimental four-step long lines: set DFFT_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("precision", [dfft.DOUBLE, dfft.FLOAT])
+def test_four_step_long_lines(precision, monkeypatch):
+    """Lines longer than one shared-memory line go through the two-pass four-step plan (DFFT_EXPERIMENTAL_LONG=1):
+    the lengths the reference's Test_1D sweep reaches with multi-upload axes (runTest1D_opt.sh:5-21)."""
+    monkeypatch.setenv("DFFT_EXPERIMENTAL_LONG", "1")
+    tol = 1e-12 if precision == dfft.DOUBLE else 5e-6
+    rng = np.random.default_rng(23)
+    for n in (8192, 16384, 131072, 6561, 19683, 78125, 16807, 12000):
+        a = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))).astype(CDT[precision][0])
+        plan = dfft.LinesPlan(n, 1, 3, 3, n, 0, precision)
+        for direction in (FORWARD, BACKWARD):
+            ref = np.fft.fft(a.astype(np.complex128), axis=1) if direction == FORWARD else np.fft.ifft(a.astype(np.complex128), axis=1) * n
+            t = _dev_array(a.reshape(-1), precision)
+            plan.execute(t.data_ptr(), direction); plan.synchronize()
+            err = np.abs(t.cpu().numpy().reshape(3, n) - ref).max() / np.abs(ref).max()
+            assert err <= tol * np.log2(n), (n, direction, err)
+        plan.destroy()
