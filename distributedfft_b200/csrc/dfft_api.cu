@@ -357,6 +357,8 @@ struct dfft_plan_s {
     bool inplace = false;
     const SizeEntry *ez = nullptr, *ey = nullptr, *ex = nullptr;   // axes N2 (Z), N1 (Y), N0 (X)
     void *lut_z = nullptr, *lut_y = nullptr, *lut_x = nullptr;
+    void* lut_xn = nullptr;   // X axis with the strided-local schedule (DFFT_NATURAL_SPECTRUM)
+    bool natural = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // per pass (Z, Y, X) brackets
@@ -607,6 +609,7 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->lut_z) cudaFree(p->lut_z);
     if (p->lut_y) cudaFree(p->lut_y);
     if (p->lut_x) cudaFree(p->lut_x);
+    if (p->lut_xn) cudaFree(p->lut_xn);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& pe : p->pev) for (auto& e : pe) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -627,11 +630,11 @@ extern "C" int dfft_memcpy(void* dst, const void* src, size_t bytes, int kind)
 // pass launches
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Pass {
-    static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a)
+    static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a, int axis_override = -1)
     {
         a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
         a.gen = e->gen;
-        const int axis = kind == PK_Z ? 0 : (kind == PK_Y || kind == PK_Y_CO || kind == PK_Y_CI ? 1 : 2);
+        const int axis = axis_override >= 0 ? axis_override : (kind == PK_Z ? 0 : (kind == PK_Y || kind == PK_Y_CO || kind == PK_Y_CI ? 1 : 2));
         cudaEventRecord(p->pev[axis][0], p->stream);
         cudaError_t err = e->launch[kind](&a, p->sms, p->stream);
         cudaEventRecord(p->pev[axis][1], p->stream);
@@ -746,6 +749,17 @@ template <typename T> struct Pass {
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "overlapped forward launch (N=%d) failed: %s", e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
+    }
+    // X transform that keeps the natural [x][y][z] layout (single device): columns along x, stride N1*N2, src -> dst
+    static int x_natural(dfft_plan p, const void* src, void* dst)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ex->s_C;
+        a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_xn;
+        a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = g.n1 * a.G;
+        a.ia = Affine{g.n2, C, 1, g.n1 * g.n2}; a.oa = a.ia;
+        return launch(p, p->ex, PK_Y, a, 2);   // a strided-local kernel, timed as the X pass
     }
     // forward X: src = [x][y_l][z] -> dst = [y_l][z][x]
     static int x_fwd(dfft_plan p, const void* src, void* dst)
@@ -868,7 +882,8 @@ template <typename T> static int execute_fused(dfft_plan p)
             }
             CU(cudaEventRecord(p->ev[1], p->stream));
             CU(cudaEventRecord(p->ev[2], p->stream));
-            if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
+            if (p->natural) { if ((rc = Pass<T>::x_natural(p, p->work, p->buf2))) return rc; }
+            else if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
@@ -915,7 +930,8 @@ template <typename T> static int execute_fused(dfft_plan p)
     } else {
         const bool scale = (p->flags & DFFT_SCALE_BACKWARD) != 0;
         if (P == 1) {
-            if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
+            if (p->natural) { if ((rc = Pass<T>::x_natural(p, p->buf1, p->buf2))) return rc; }
+            else if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
             CU(cudaEventRecord(p->ev[1], p->stream));
             CU(cudaEventRecord(p->ev[2], p->stream));
             if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, p->buf2, p->buf2, nullptr, 0, nullptr, scale))) return rc; }

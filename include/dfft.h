@@ -52,6 +52,8 @@ extern "C" {
                                     Default: fused when the exchange is P2P (the Y stores are NVLink-bound and hide the
                                     Z role), two sweeps otherwise */
 
+#define DFFT_NATURAL_SPECTRUM 64u /* EXPERIMENTAL, single device: the spectrum (forward output / backward input) is kept in natural
+                                    [x][y][z] order instead of the reference's transposed [y][z][x] */
 #define DFFT_OVERLAP_X 32u       /* EXPERIMENTAL (forward, P2P, square planes): the whole transform of a device as one kernel;
                                     the z axis is sent in parts and the X lines of a part start as soon as it has arrived
                                     from every sender, overlapping t3 with the NVLink-bound sends (env DFFT_OVERLAP=1) */

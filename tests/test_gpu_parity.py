@@ -397,3 +397,16 @@ def test_four_step_long_lines(precision, monkeypatch):
             err = np.abs(t.cpu().numpy().reshape(3, n) - ref).max() / np.abs(ref).max()
             assert err <= tol * np.log2(n), (n, direction, err)
         plan.destroy()
+
+
+@pytest.mark.skipif(os.environ.get("DFFT_TEST_EXPERIMENTAL") != "1", reason="experimental natural-order spectrum: set DFFT_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("n0,n1,n2", [(16, 32, 8), (48, 64, 64), (15, 22, 26)])
+def test_natural_order_spectrum_single_device(n0, n1, n2):
+    """DFFT_NATURAL_SPECTRUM: forward output / backward input in natural [x][y][z] order."""
+    rng = np.random.default_rng(n0 + n2)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    ref = np.fft.fftn(A).reshape(-1)
+    f = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)], flags=dfft.NATURAL_SPECTRUM)
+    assert np.abs(f[0]["buf2"] - ref).max() <= 1e-12 * np.log2(A.size) * np.abs(ref).max()
+    b = run_slab(n0, n1, n2, 1, BACKWARD, [ref], flags=dfft.NATURAL_SPECTRUM)
+    assert np.abs(b[0]["buf2"] / A.size - A.reshape(-1)).max() <= 1e-11
