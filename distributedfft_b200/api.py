@@ -33,7 +33,7 @@ __all__ = [
     "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "OVERLAP_X", "NATURAL_SPECTRUM", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
-    "fft_lines", "LinesPlan", "length_kind", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
+    "fft_lines", "LinesPlan", "length_kind", "length_schedule", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
 ]
 
 
@@ -93,6 +93,9 @@ def lib():
     L.dfft_lines_stream.argtypes = [vp]
     L.dfft_lines_stream.restype = vp
     L.dfft_length_kind.argtypes = [i, i]
+    L.dfft_length_schedule.argtypes = [i, i, P(ctypes.c_int), i]
+    L.dfft_debug_fused3_order.argtypes = [ll, ll, i, i, i, i, i, ll, P(ll)]
+    L.dfft_debug_fused3_order.restype = ll
     L.dfft_memcpy.argtypes = [vp, vp, ctypes.c_size_t, i]
     _lib = L
     return L
@@ -113,6 +116,13 @@ def supported_lengths(precision=DOUBLE):
 def length_kind(n, precision=DOUBLE):
     """2 = tuned kernel, 1 = run-time-scheduled kernel (2..13-smooth lengths), 0 = unsupported."""
     return int(lib().dfft_length_kind(n, precision))
+
+
+def length_schedule(n, precision=DOUBLE):
+    """radix list the library uses for length n ([] if unsupported)"""
+    arr = (ctypes.c_int * 32)()
+    k = lib().dfft_length_schedule(n, precision, arr, 32)
+    return list(arr[:k])
 
 
 def getMaxDataCount(n0, n1, n2, totalDevCount, isLastDevice):

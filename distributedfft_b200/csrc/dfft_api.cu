@@ -56,6 +56,33 @@ extern "C" int dfft_length_kind(int n, int precision)
     return !e ? 0 : (e->gen ? 1 : 2);
 }
 
+/* radix schedule the library uses for length n (contiguous-pass schedule for tuned lengths, the run-time schedule for
+ * generic ones); returns the number of stages, 0 if unsupported */
+extern "C" int dfft_length_schedule(int n, int precision, int* radices, int max_radices)
+{
+    if (n < 1 || n > (1 << 20) || (precision != DFFT_DOUBLE && precision != DFFT_FLOAT)) return 0;
+    const SizeEntry* e = find_size_entry(n, precision);
+    if (!e) return 0;
+    if (radices)
+        for (int i = 0; i < e->z_nstages && i < max_radices; i++) radices[i] = e->z_rad[i];
+    return e->z_nstages;
+}
+
+/* test hook (host only, no device needed): ticket -> (role, part, plane, tile) of the single-kernel forward path;
+ * ticket < 0 returns the number of tickets */
+extern "C" long long dfft_debug_fused3_order(long long planes, long long rows, int GA, int GBk, int GXk, int K, int lag, long long ticket, long long out[4])
+{
+    Fused3Ctl F{};
+    F.planes = planes; F.rows = rows; F.GA = GA; F.GBk = GBk; F.GB = GBk * K; F.GXk = GXk; F.GX = GXk * K; F.K = K; F.lag = lag;
+    const long long total = fused3_total(F);
+    if (ticket < 0 || ticket >= total || !out) return total;
+    int role, part;
+    long long plane, idx;
+    fused3_decode(F, ticket, role, part, plane, idx);
+    out[0] = role; out[1] = part; out[2] = plane; out[3] = idx;
+    return total;
+}
+
 extern "C" int dfft_supported_lengths(int precision, int* lengths, int max_lengths)
 {
     std::vector<int> v;

@@ -473,6 +473,55 @@ struct Fused3Ctl {
     int lag;
 };
 
+// Ticket order of fft_fused3_kernel (host-callable so that the CPU tests can check it is a bijection onto the tiles
+// and respects the dependency order):
+//   phase 0        : Z on every plane + Y part 0, interleaved like fft_fused2_kernel (Z runs `lag` planes ahead)
+//   phase k = 1..K-1: Y part k (LY tiles, plane-major) merged with X part k-1 (LX tiles); the X tiles start after a
+//                    quarter of the phase's Y tiles and are then spread evenly
+//   tail           : X part K-1
+__host__ __device__ inline long long fused3_total(const Fused3Ctl& F)
+{
+    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
+    return F.planes * ((long long)F.GA + F.GBk) + (long long)(F.K - 1) * (LY + LX) + LX;
+}
+__host__ __device__ inline void fused3_decode(const Fused3Ctl& F, long long t, int& role, int& part, long long& plane, long long& idx)
+{
+    const long long lag = F.lag < F.planes ? F.lag : F.planes;
+    const long long headT = lag * F.GA;
+    const long long midT = (F.planes - lag) * ((long long)F.GA + F.GBk);
+    const long long L0 = headT + midT + lag * F.GBk;
+    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
+    const long long dly = LY / 4, LM = LY - dly + LX;
+    part = 0; plane = 0; idx = 0;
+    if (t < L0) {
+        if (t < headT) { role = 0; plane = t / F.GA; idx = t - plane * F.GA; }
+        else if (t < headT + midT) {
+            const long long u = t - headT, i = u / (F.GA + F.GBk), r = u - i * (F.GA + F.GBk);
+            if (r < F.GA) { role = 0; plane = lag + i; idx = r; }
+            else { role = 1; plane = i; idx = r - F.GA; }
+        } else {
+            const long long u = t - headT - midT, i = u / F.GBk;
+            role = 1; plane = F.planes - lag + i; idx = u - i * F.GBk;
+        }
+        return;
+    }
+    const long long u0 = t - L0;
+    const long long ph = u0 / (LY + LX);          // 0-based: phase ph+1, or >= K-1 for the final X part
+    const long long u = u0 - ph * (LY + LX);
+    if (ph >= F.K - 1) { role = 2; part = F.K - 1; idx = u; return; }
+    long long yi;
+    bool isx = false;
+    if (u < dly) yi = u;
+    else {
+        const long long v = u - dly;
+        const long long xc0 = v * LX / LM, xc1 = (v + 1) * LX / LM;   // X tiles placed before position v / v+1
+        if (xc1 > xc0) { isx = true; yi = xc0; }
+        else yi = dly + v - xc0;
+    }
+    if (isx) { role = 2; part = (int)ph; idx = yi; }
+    else { role = 1; part = (int)ph + 1; plane = yi / F.GBk; idx = yi - plane * F.GBk; }
+}
+
 template <class OpA, class OpB, class OpC, typename T, int MINB>
 __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArgs<T> A, const TileArgs<T> B, const TileArgs<T> Cc, const Fused3Ctl F)
 {
@@ -492,53 +541,16 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
     OpB::load_twiddles(kb, twb);
     OpC::load_twiddles(kc, twc);
 
-    const long long lag = F.lag < F.planes ? F.lag : F.planes;
-    // phase 0: Z on every plane + Y part 0, interleaved like fft_fused2_kernel
-    const long long headT = lag * F.GA;
-    const long long midT = (F.planes - lag) * ((long long)F.GA + F.GBk);
-    const long long L0 = headT + midT + lag * F.GBk;
-    // phases 1..K-1: Y part k (LY tiles) merged with X part k-1 (LX tiles); X starts after a quarter of the Y tiles
-    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
-    const long long dly = LY / 4, LM = LY - dly + LX;
-    const long long total = L0 + (long long)(F.K - 1) * (LY + LX) + LX;
+    const long long total = fused3_total(F);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(F.ticket, 1u);
         __syncthreads();
         const long long t = s_ticket;
         if (t >= total) break;
-        int role;            // 0 = Z, 1 = Y, 2 = X
-        int part = 0;
-        long long plane = 0, idx = 0;   // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
-        if (t < L0) {
-            if (t < headT) { role = 0; plane = t / F.GA; idx = t - plane * F.GA; }
-            else if (t < headT + midT) {
-                const long long u = t - headT, i = u / (F.GA + F.GBk), r = u - i * (F.GA + F.GBk);
-                if (r < F.GA) { role = 0; plane = lag + i; idx = r; }
-                else { role = 1; plane = i; idx = r - F.GA; }
-            } else {
-                const long long u = t - headT - midT, i = u / F.GBk;
-                role = 1; plane = F.planes - lag + i; idx = u - i * F.GBk;
-            }
-        } else {
-            const long long u0 = t - L0;
-            const long long ph = u0 / (LY + LX);          // 0-based: phase ph+1, or K-1 for the final X part
-            const long long u = u0 - ph * (LY + LX);
-            if (ph >= F.K - 1) { role = 2; part = F.K - 1; idx = u; }
-            else {
-                long long yi;
-                bool isx = false;
-                if (u < dly) yi = u;
-                else {
-                    const long long v = u - dly;
-                    const long long xc0 = v * LX / LM, xc1 = (v + 1) * LX / LM;   // X tiles placed before position v / v+1
-                    if (xc1 > xc0) { isx = true; yi = xc0; }
-                    else yi = dly + v - xc0;
-                }
-                if (isx) { role = 2; part = (int)ph; idx = yi; }
-                else { role = 1; part = (int)ph + 1; plane = yi / F.GBk; idx = yi - plane * F.GBk; }
-            }
-        }
+        int role, part;          // role 0 = Z, 1 = Y, 2 = X
+        long long plane, idx;    // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
+        fused3_decode(F, t, role, part, plane, idx);
         if (role == 0) {
             OpA::run(A, ka, plane * F.GA + idx, twa);
             __syncthreads();

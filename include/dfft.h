@@ -80,6 +80,12 @@ int dfft_version(void);
  * 12800 in float, i.e. while two copies of a line fit in shared memory); 0: unsupported (other primes, or longer:
  * the reference switches to multi-upload passes there, templateFFT.cpp:4007-4106, which this library does not have) */
 int dfft_length_kind(int n, int precision);
+/* radix schedule used for length n (stage order as executed); returns the number of stages, 0 if unsupported */
+int dfft_length_schedule(int n, int precision, int* radices, int max_radices);
+/* test hook (host only): ticket order of the single-kernel forward path (fft_fused3_kernel); out = role (0 Z, 1 Y, 2 X),
+ * part, plane, tile; returns the number of tickets (ticket < 0: only that) */
+long long dfft_debug_fused3_order(long long planes, long long rows, int GA, int GBk, int GXk, int K, int lag, long long ticket,
+                                  long long out[4]);
 /* number of TUNED transform lengths for a precision; fills `lengths` (may be NULL) */
 int dfft_supported_lengths(int precision, int* lengths, int max_lengths);
 

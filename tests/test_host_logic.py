@@ -131,3 +131,58 @@ def test_bootstrap_comm_world2_gloo(tmp_path):
                         "--master-port", "29571", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_length_policy_matches_the_reference_generator():
+    """Lengths: tuned table, run-time-scheduled 2..13-smooth lengths with the reference's radix policy
+    (templateFFT.cpp:3956-3963 factor over 2..13, :4540-4550 merge 2s into 8s then 4s, :4580-4588 descending order --
+    restated independently in oracle_fft.c), everything else rejected."""
+    co = COracle()
+    for n in (512, 768, 1024, 64, 100):
+        assert dfft.length_kind(n) == 2 and dfft.length_kind(n, dfft.FLOAT) == 2
+        assert int(np.prod(dfft.length_schedule(n))) == n
+    for n in (2, 3, 5, 7, 11, 13, 15, 30, 77, 143, 360, 1001, 2187, 3000, 3125, 6400, 6144):
+        assert dfft.length_kind(n) == 1, n
+        assert dfft.length_schedule(n) == co.radix_schedule(n), n
+    for n in (17, 19, 34, 6561, 8192, 1 << 21):
+        assert dfft.length_kind(n) == 0 and dfft.length_schedule(n) == []
+    assert dfft.length_kind(8192, dfft.FLOAT) == 1 and dfft.length_kind(12800, dfft.FLOAT) == 1 and dfft.length_kind(16384, dfft.FLOAT) == 0
+
+
+@pytest.mark.parametrize("planes,rows,GA,GBk,GXk,K,lag", [(64, 64, 128, 16, 16, 4, 3), (5, 7, 3, 2, 1, 2, 2), (8, 3, 4, 1, 5, 8, 100), (1, 1, 1, 1, 1, 1, 1),
+                                                      (6, 6, 2, 3, 3, 1, 2)])
+def test_single_kernel_forward_ticket_order(planes, rows, GA, GBk, GXk, K, lag):
+    """The ticket order of the single-kernel forward path (fft_fused3_kernel) must hand out every Z, Y and X tile
+    exactly once, and every dependency must have a lower ticket: Z tiles of a plane before its Y tiles, all Y tiles of
+    part k (on this device) before any X tile of part k."""
+    import ctypes
+    L = dfft.lib()
+    out = (ctypes.c_longlong * 4)()
+    total = L.dfft_debug_fused3_order(planes, rows, GA, GBk, GXk, K, lag, -1, out)
+    assert total == planes * (GA + GBk * K) + rows * GXk * K
+    seen = set()
+    last_z = {}        # plane -> highest ticket of its Z tiles
+    last_y = {}        # part -> highest ticket of its Y tiles
+    first_y = {}       # plane -> lowest ticket of its Y tiles
+    first_x = {}       # part -> lowest ticket of its X tiles
+    for t in range(total):
+        assert L.dfft_debug_fused3_order(planes, rows, GA, GBk, GXk, K, lag, t, out) == total
+        role, part, plane, idx = (int(x) for x in out)
+        key = (role, part, plane, idx)
+        assert key not in seen, key
+        seen.add(key)
+        if role == 0:
+            assert 0 <= plane < planes and 0 <= idx < GA and part == 0
+            last_z[plane] = t
+        elif role == 1:
+            assert 0 <= plane < planes and 0 <= idx < GBk and 0 <= part < K
+            last_y[part] = t
+            first_y.setdefault(plane, t)
+        else:
+            assert role == 2 and 0 <= idx < rows * GXk and 0 <= part < K
+            first_x.setdefault(part, t)
+    assert len(seen) == total
+    for plane in range(planes):
+        assert last_z[plane] < first_y[plane]
+    for part in range(K):
+        assert last_y[part] < first_x[part]
