@@ -24,16 +24,17 @@ NO_FUSE = 8
 FORCE_FUSE = 16
 OVERLAP_X = 32
 NATURAL_SPECTRUM = 64
+DRY_RUN = 128
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfft.so")
 
 __all__ = [
     "FORWARD", "BACKWARD", "ALLOC_CPU", "ALLOC_DEV", "DOUBLE", "FLOAT", "EXCHANGE_AUTO", "EXCHANGE_P2P",
-    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "OVERLAP_X", "NATURAL_SPECTRUM", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
+    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "OVERLAP_X", "NATURAL_SPECTRUM", "DRY_RUN", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
-    "fft_lines", "LinesPlan", "length_kind", "length_schedule", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
+    "fft_lines", "lines_ops", "LinesPlan", "length_kind", "length_schedule", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
 ]
 
 
@@ -93,6 +94,10 @@ def lib():
     L.dfft_lines_stream.argtypes = [vp]
     L.dfft_lines_stream.restype = vp
     L.dfft_length_kind.argtypes = [i, i]
+    L.dfft_debug_plan_ops.argtypes = [vp, ctypes.c_char_p, ll]
+    L.dfft_debug_plan_ops.restype = ll
+    L.dfft_debug_lines_ops.argtypes = [i, ll, ll, ll, ll, ll, i, i, i, ctypes.c_char_p, ll]
+    L.dfft_debug_lines_ops.restype = ll
     L.dfft_length_schedule.argtypes = [i, i, P(ctypes.c_int), i]
     L.dfft_debug_fused3_order.argtypes = [ll, ll, i, i, i, i, i, ll, P(ll)]
     L.dfft_debug_fused3_order.restype = ll
@@ -267,6 +272,14 @@ class Plan:
     def fused(self):
         return bool(lib().dfft_plan_fused(self.handle))
 
+    def recorded_ops(self):
+        """passes recorded by the last execute of a DRY_RUN plan (list of dicts)"""
+        import json
+        n = lib().dfft_debug_plan_ops(self.handle, None, 0)
+        buf = ctypes.create_string_buffer(int(n))
+        lib().dfft_debug_plan_ops(self.handle, buf, n)
+        return json.loads(buf.value.decode())
+
     @property
     def overlapped(self):
         """forward transform runs as the single overlapped kernel (OVERLAP_X, experimental)"""
@@ -334,6 +347,17 @@ class LinesPlan:
         if self.handle:
             lib().dfft_lines_destroy(self.handle)
             self.handle = None
+
+
+def lines_ops(n, stride, nlines, inner, inner_dist, outer_dist, direction, precision=DOUBLE, two_d=False):
+    """passes a lines plan would launch (host-only test hook, see dfft_debug_lines_ops)"""
+    import json
+    need = lib().dfft_debug_lines_ops(n, stride, nlines, inner, inner_dist, outer_dist, precision, direction, int(two_d), None, 0)
+    if need < 0:
+        raise DfftError("dfft_debug_lines_ops: " + lib().dfft_last_error().decode())
+    buf = ctypes.create_string_buffer(int(need))
+    lib().dfft_debug_lines_ops(n, stride, nlines, inner, inner_dist, outer_dist, precision, direction, int(two_d), buf, need)
+    return json.loads(buf.value.decode())
 
 
 def fft_lines(ptr, n, stride, nlines, inner, inner_dist, outer_dist, direction, precision=DOUBLE):

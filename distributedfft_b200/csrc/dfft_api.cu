@@ -406,6 +406,10 @@ struct dfft_plan_s {
     unsigned long long* plane_done = nullptr;
     unsigned int* ticket = nullptr;
     unsigned long long fuse_epoch = 0;
+    // describe-only plans (DFFT_DRY_RUN): no CUDA call is made, buffers are symbolic addresses, execute records the
+    // passes it would launch (dfft_debug_plan_ops) -- lets the CPU tests interpret the whole multi-device schedule
+    bool dry = false;
+    std::vector<std::string> ops;
     // overlapped forward (fft_fused3_kernel): own intermediate buffer, per-part counters
     bool overlap = false;
     int parts = 1;
@@ -413,6 +417,38 @@ struct dfft_plan_s {
     unsigned long long* part_done = nullptr;
     unsigned long long overlap_epoch = 0;
 };
+
+// symbolic device address of a describe-only plan: device d (0-based), buffer id b: 1 bufferDev1, 2 bufferDev2 / user out,
+// 3 work / receive buffer, 4 intermediate of the single-kernel path, 5 user in
+static inline void* fake_addr(int d, int b) { return (void*)((((unsigned long long)(d + 1)) << 44) | (((unsigned long long)b) << 40)); }
+static inline cudaError_t ev_record(dfft_plan p, cudaEvent_t e) { return p->dry ? cudaSuccess : ev_record(p, e); }
+
+template <typename T>
+static void record_op(dfft_plan p, const char* name, int phase, int N, int C, bool chunk_in, bool chunk_out, bool transposed_store, const TileArgs<T>& a)
+{
+    char buf[256];
+    std::string o = "{";
+    snprintf(buf, sizeof(buf), "\"op\": \"%s\", \"phase\": %d, \"N\": %d, \"C\": %d, \"G\": %d, \"W\": %d, \"ntiles\": %lld, \"inv\": %d, \"do_scale\": %d, \"scale\": %.17g, \"tw_n\": %lld, ",
+             name, phase, N, C, a.G, a.W, a.ntiles, a.inv, a.do_scale, (double)a.scale, a.tw_n);
+    o += buf;
+    snprintf(buf, sizeof(buf), "\"in\": %llu, \"out\": %llu, \"ia\": [%lld, %lld, %lld, %lld], \"oa\": [%lld, %lld, %lld, %lld], \"tstore\": %d",
+             (unsigned long long)(size_t)a.in, (unsigned long long)(size_t)a.out, a.ia.SA, a.ia.SB, a.ia.cs, a.ia.es, a.oa.SA, a.oa.SB, a.oa.cs, a.oa.es,
+             transposed_store ? 1 : 0);
+    o += buf;
+    for (int side = 0; side < 2; side++) {
+        const bool on = side == 0 ? chunk_in : chunk_out;
+        if (!on) continue;
+        const ChunkTab& ct = side == 0 ? a.ci : a.co;
+        snprintf(buf, sizeof(buf), ", \"%s\": {\"ediv\": %d, \"nchunks\": %d, \"cptr\": [", side == 0 ? "ci" : "co", ct.ediv, ct.nchunks);
+        o += buf;
+        for (int q = 0; q < ct.nchunks; q++) { snprintf(buf, sizeof(buf), "%s%llu", q ? ", " : "", (unsigned long long)(size_t)ct.cptr[q]); o += buf; }
+        o += "], \"SAq\": [";
+        for (int q = 0; q < ct.nchunks; q++) { snprintf(buf, sizeof(buf), "%s%lld", q ? ", " : "", ct.SAq[q]); o += buf; }
+        o += "]}";
+    }
+    o += "}";
+    p->ops.push_back(o);
+}
 
 template <typename T> static void upload_lut(void** dst, int nstages, const int* rad)
 {
@@ -426,6 +462,7 @@ static int share_pointer(dfft_plan p, void* mine, std::vector<void*>& peers)
     // make `mine` (a cudaMalloc allocation of this device) addressable by every rank
     const int P = p->P;
     peers.assign(P, nullptr);
+    if (p->dry) return 0;   // describe-only plans compute peer addresses symbolically
     if (p->comm->local) {
         std::vector<void*> all(P);
         p->comm->allgather(p->me, &mine, all.data(), sizeof(void*));
@@ -456,7 +493,8 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     if (direction != DFFT_FORWARD && direction != DFFT_BACKWARD) return fail(DFFT_EINVAL, "direction must be +1 or -1");
     if (precision != DFFT_DOUBLE && precision != DFFT_FLOAT) return fail(DFFT_EINVAL, "bad precision");
     if (P > DFFT_MAX_CHUNKS) return fail(DFFT_EUNSUPPORTED, "at most %d devices", DFFT_MAX_CHUNKS);
-    if (P > 1 && (!comm || comm->nranks != P)) return fail(DFFT_EINVAL, "a communicator of %d ranks is required", P);
+    const bool dry = (flags & DFFT_DRY_RUN) != 0;
+    if (!dry && P > 1 && (!comm || comm->nranks != P)) return fail(DFFT_EINVAL, "a communicator of %d ranks is required", P);
     Geom g{n0, n1, n2, P};
     if (g.last_n0() < 1 || g.last_n1() < 1)
         return fail(DFFT_EUNSUPPORTED, "%lldx%lldx%lld cannot be split over %d devices (empty last slab); use dfft_init", n0, n1, n2, P);
@@ -475,6 +513,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     p->max_count = g.max_count(dev_idx);
     p->ez = ez; p->ey = ey; p->ex = ex; p->comm = comm;
     p->in = in; p->out = out;
+    p->dry = dry;
     int rc = 0;
     auto bail = [&](int code) { dfft_destroy(p); return code; };
 #define CUP(x)                                                                                        \
@@ -482,17 +521,24 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         cudaError_t e_ = (x);                                                                         \
         if (e_ != cudaSuccess) return bail(fail(DFFT_ECUDA, "%s:%d CUDA call '%s' failed: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_))); \
     } while (0)
-    CUP(cudaGetDevice(&p->device));
-    CUP(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    if (!dry) {
+        CUP(cudaGetDevice(&p->device));
+        CUP(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    }
     // buffers (api.cpp:66-77)
     if (!out || out == in) { p->inplace = true; p->buf2 = in; }
     else p->buf2 = out;
-    CUP(cudaMalloc(&p->buf1, (size_t)p->max_count * p->esz));
-    CUP(cudaMemcpy(p->buf1, in, (size_t)p->max_count * p->esz, cudaMemcpyDeviceToDevice));
-    CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    for (auto& e : p->ev) CUP(cudaEventCreate(&e));
-    for (auto& pe : p->pev) for (auto& e : pe) CUP(cudaEventCreate(&e));
-    if (precision == DFFT_DOUBLE) {
+    if (dry) p->buf1 = fake_addr(dev_idx, 1);
+    else {
+        CUP(cudaMalloc(&p->buf1, (size_t)p->max_count * p->esz));
+        CUP(cudaMemcpy(p->buf1, in, (size_t)p->max_count * p->esz, cudaMemcpyDeviceToDevice));
+        CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        for (auto& e : p->ev) CUP(cudaEventCreate(&e));
+        for (auto& pe : p->pev) for (auto& e : pe) CUP(cudaEventCreate(&e));
+    }
+    if (dry) {
+        // no twiddle tables: the interpreter of the recorded passes does its own transforms
+    } else if (precision == DFFT_DOUBLE) {
         upload_lut<double>(&p->lut_z, ez->z_nstages, ez->z_rad);
         upload_lut<double>(&p->lut_y, ey->s_nstages, ey->s_rad);
         upload_lut<double>(&p->lut_x, ex->x_nstages, ex->x_rad);
@@ -501,7 +547,18 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         upload_lut<float>(&p->lut_y, ey->s_nstages, ey->s_rad);
         upload_lut<float>(&p->lut_x, ex->x_nstages, ex->x_rad);
     }
-    CUP(cudaGetLastError());
+    if (!dry) CUP(cudaGetLastError());
+    if (flags & DFFT_NATURAL_SPECTRUM) {
+        // spectrum kept in natural [x][y][z] order: one device only (with P > 1 it would need a second all-to-all)
+        if (P != 1) return bail(fail(DFFT_EUNSUPPORTED, "DFFT_NATURAL_SPECTRUM needs a single device (a distributed natural-order spectrum would take a second exchange)"));
+        if ((flags & DFFT_EXCHANGE_MASK) == DFFT_EXCHANGE_STAGED) return bail(fail(DFFT_EINVAL, "DFFT_NATURAL_SPECTRUM cannot be combined with the staged mode"));
+        p->natural = true;
+        if (!dry) {
+            if (precision == DFFT_DOUBLE) upload_lut<double>(&p->lut_xn, ex->s_nstages, ex->s_rad);
+            else upload_lut<float>(&p->lut_xn, ex->s_nstages, ex->s_rad);
+            CUP(cudaGetLastError());
+        }
+    }
     // exchange mode
     int xmode = (int)(flags & DFFT_EXCHANGE_MASK);
     if (P == 1) xmode = xmode == DFFT_EXCHANGE_STAGED ? DFFT_EXCHANGE_STAGED : DFFT_EXCHANGE_P2P;
@@ -511,7 +568,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         else if (env && !strcmp(env, "staged")) xmode = DFFT_EXCHANGE_STAGED;
         else xmode = DFFT_EXCHANGE_P2P;
     }
-    if (P > 1) {
+    if (P > 1 && !dry) {
         // peer reachability (api.cpp:16-27 enables peer access in fft_mpi_init; done here so a plan does not
         // depend on dfft_init having run).  Threads of one process map peers directly and need
         // cudaDeviceEnablePeerAccess; separate processes get it from cudaIpcOpenMemHandle.
@@ -550,7 +607,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         if (flags & DFFT_NO_FUSE) want = false;
         p->fuse = can && want;
         if (getenv("DFFT_LAG")) p->lag = atoi(getenv("DFFT_LAG"));
-        if (p->fuse) {
+        if (p->fuse && !dry) {
             CUP(cudaMalloc((void**)&p->plane_done, (size_t)p->n0l * sizeof(unsigned long long)));
             CUP(cudaMemset(p->plane_done, 0, (size_t)p->n0l * sizeof(unsigned long long)));
             CUP(cudaMalloc((void**)&p->ticket, 2 * sizeof(unsigned int)));
@@ -558,7 +615,9 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         }
     }
 
-    if (xmode != DFFT_EXCHANGE_STAGED) CUP(cudaMalloc(&p->work, (size_t)p->max_count * p->esz));
+    if (dry && xmode == DFFT_EXCHANGE_STAGED) return bail(fail(DFFT_EINVAL, "DFFT_DRY_RUN cannot describe the staged mode"));
+    if (dry) p->work = fake_addr(dev_idx, 3);
+    else if (xmode != DFFT_EXCHANGE_STAGED) CUP(cudaMalloc(&p->work, (size_t)p->max_count * p->esz));
     {
         // opt-in: the whole forward transform of a device as one kernel with t3 overlapped behind per-part arrivals
         const char* env = getenv("DFFT_OVERLAP");
@@ -576,13 +635,19 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
                 }
                 p->parts = K;
                 p->overlap = true;
-                CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
-                CUP(cudaMalloc((void**)&p->part_done, DFFT_MAX_PARTS * sizeof(unsigned long long)));
-                CUP(cudaMemset(p->part_done, 0, DFFT_MAX_PARTS * sizeof(unsigned long long)));
+                if (dry) p->mid = fake_addr(dev_idx, 4);
+                else {
+                    CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
+                    CUP(cudaMalloc((void**)&p->part_done, DFFT_MAX_PARTS * sizeof(unsigned long long)));
+                    CUP(cudaMemset(p->part_done, 0, DFFT_MAX_PARTS * sizeof(unsigned long long)));
+                }
             }
         }
     }
-    if (P > 1) {
+    if (P > 1 && dry) {
+        p->peer_work.resize(P);
+        for (int q = 0; q < P; q++) p->peer_work[q] = fake_addr(q, 3);
+    } else if (P > 1) {
         if (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_STAGED) {
             if (xmode == DFFT_EXCHANGE_P2P) {
                 if ((rc = share_pointer(p, p->work, p->peer_work)) != 0) return bail(rc);
@@ -611,7 +676,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         }
         comm->host_barrier(p->me);
     }
-    CUP(cudaDeviceSynchronize());
+    if (!dry) CUP(cudaDeviceSynchronize());
 #undef CUP
     *plan_out = p;
     return 0;
@@ -620,6 +685,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
 extern "C" int dfft_destroy(dfft_plan p)
 {
     if (!p) return 0;
+    if (p->dry) { delete p; return 0; }   // nothing was allocated
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->P > 1 && p->comm && (p->sync || p->nccl)) p->comm->host_barrier(p->me);   // nobody still writes into my buffers
@@ -662,9 +728,19 @@ template <typename T> struct Pass {
         a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
         a.gen = e->gen;
         const int axis = axis_override >= 0 ? axis_override : (kind == PK_Z ? 0 : (kind == PK_Y || kind == PK_Y_CO || kind == PK_Y_CI ? 1 : 2));
-        cudaEventRecord(p->pev[axis][0], p->stream);
+        if (p->dry) {
+            static const char* names[PK_COUNT] = {"Z", "Y", "Y_CO", "Y_CI", "XF", "XB", "XB_CO", "XF_TW"};
+            const int C = kind == PK_Z ? e->z_C : (kind == PK_Y || kind == PK_Y_CI ? e->s_C : (kind == PK_Y_CO ? e->p_C : e->x_C));
+            // phase 1 = runs after the exchange has delivered this device's receive buffer
+            const bool fwd = p->direction == DFFT_FORWARD;
+            const int phase = fwd ? (axis == 2 ? 1 : 0) : (axis == 2 ? 0 : 1);
+            record_op<T>(p, names[kind], phase, e->N, C, kind == PK_Y_CI, kind == PK_Y_CO || kind == PK_XB_CO, kind == PK_XF || kind == PK_XF_TW, a);
+            p->launches++;
+            return 0;
+        }
+        ev_record(p, p->pev[axis][0]);
         cudaError_t err = e->launch[kind](&a, p->sms, p->stream);
-        cudaEventRecord(p->pev[axis][1], p->stream);
+        ev_record(p, p->pev[axis][1]);
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "pass launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
@@ -729,11 +805,18 @@ template <typename T> struct Pass {
         c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
         c.lag = p->lag;
         const int kind = fwd ? (ymode == 1 ? FK_ZY_CO : FK_ZY) : (ymode == 2 ? FK_YZ_CI : FK_YZ);
-        cudaEventRecord(p->pev[0][0], p->stream);
+        if (p->dry) {
+            z.gen = y.gen = nullptr;
+            if (fwd) { record_op<T>(p, "fusedZ", 0, e->N, CZ, false, false, false, z); record_op<T>(p, "fusedY", 0, e->N, CY, false, ymode == 1, false, y); }
+            else { record_op<T>(p, "fusedY", 1, e->N, CY, ymode == 2, false, false, y); record_op<T>(p, "fusedZ", 1, e->N, CZ, false, false, false, z); }
+            p->launches++;
+            return 0;
+        }
+        ev_record(p, p->pev[0][0]);
         cudaError_t err = fwd ? e->fused[kind](&z, &y, &c, p->sms, p->stream) : e->fused[kind](&y, &z, &c, p->sms, p->stream);
-        cudaEventRecord(p->pev[0][1], p->stream);
-        cudaEventRecord(p->pev[1][0], p->stream);
-        cudaEventRecord(p->pev[1][1], p->stream);
+        ev_record(p, p->pev[0][1]);
+        ev_record(p, p->pev[1][0]);
+        ev_record(p, p->pev[1][1]);
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "fused t0 launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
@@ -769,10 +852,17 @@ template <typename T> struct Pass {
         c.my_arrive = &p->sync->part_arrive[0][0];
         for (int q = 0; q < p->P; q++) c.peer_arrive[q] = &p->peer_sync[q]->part_arrive[0][0];
         c.lag = p->lag;
-        cudaEventRecord(p->pev[0][0], p->stream);
+        if (p->dry) {
+            record_op<T>(p, "ovlZ", 0, e->N, CZ, false, false, false, z);
+            record_op<T>(p, "ovlY", 0, e->N, CY, false, true, false, y);
+            record_op<T>(p, "ovlX", 1, e->N, CX, false, false, true, x);
+            p->launches++;
+            return 0;
+        }
+        ev_record(p, p->pev[0][0]);
         cudaError_t err = e->fused3(&z, &y, &x, &c, p->sms, p->stream);
-        cudaEventRecord(p->pev[0][1], p->stream);
-        for (int a = 1; a < 3; a++) { cudaEventRecord(p->pev[a][0], p->stream); cudaEventRecord(p->pev[a][1], p->stream); }
+        ev_record(p, p->pev[0][1]);
+        for (int a = 1; a < 3; a++) { ev_record(p, p->pev[a][0]); ev_record(p, p->pev[a][1]); }
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "overlapped forward launch (N=%d) failed: %s", e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
@@ -852,6 +942,7 @@ extern "C" int dfft_exchange_table(long long n0, long long n1, long long n2, int
 
 static int flags_signal(dfft_plan p, bool arrive, unsigned long long value)
 {
+    if (p->dry) return 0;
     FlagPtrs fp{};
     for (int q = 0; q < p->P; q++) fp.p[q] = arrive ? &p->peer_sync[q]->arrive[p->me] : &p->peer_sync[q]->ready[p->me];
     signal_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, p->stream>>>(fp, p->P, value);
@@ -861,7 +952,7 @@ static int flags_signal(dfft_plan p, bool arrive, unsigned long long value)
 }
 static int flags_wait(dfft_plan p, bool arrive, unsigned long long value)
 {
-    if (value == 0) return 0;
+    if (value == 0 || p->dry) return 0;
     wait_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, p->stream>>>(arrive ? p->sync->arrive : p->sync->ready, p->P, value);
     CU(cudaGetLastError());
     p->launches++;
@@ -870,9 +961,24 @@ static int flags_wait(dfft_plan p, bool arrive, unsigned long long value)
 
 static int nccl_exchange(dfft_plan p, const void* sendbuf, void* recvbuf)
 {
-    NcclApi& api = nccl_api();
     const Geom& g = p->g;
     const int dir = p->direction;
+    if (p->dry) {   // describe the all-to-all: element offsets and counts of every chunk this device sends
+        char buf[160];
+        std::string o = "{\"op\": \"alltoall\", \"phase\": 0, ";
+        snprintf(buf, sizeof(buf), "\"send\": %llu, \"recv\": %llu, \"esz\": %zu, \"chunks\": [", (unsigned long long)(size_t)sendbuf,
+                 (unsigned long long)(size_t)recvbuf, p->esz);
+        o += buf;
+        for (int q = 0; q < p->P; q++) {
+            snprintf(buf, sizeof(buf), "%s[%d, %lld, %lld, %lld]", q ? ", " : "", q, send_off(g, p->me, q, dir), recv_off(g, p->me, q, dir), xchg_count(g, p->me, q, dir));
+            o += buf;
+        }
+        o += "]}";
+        p->ops.push_back(o);
+        p->launches++;
+        return 0;
+    }
+    NcclApi& api = nccl_api();
     bool even = true;
     for (int q = 0; q < p->P; q++)
         if (xchg_count(g, p->me, q, dir) != xchg_count(g, 0, 0, dir) || xchg_count(g, q, p->me, dir) != xchg_count(g, 0, 0, dir)) even = false;
@@ -896,7 +1002,7 @@ template <typename T> static int execute_fused(dfft_plan p)
     const int P = p->P, me = p->me;
     int rc;
     p->launches = 0;
-    CU(cudaEventRecord(p->ev[0], p->stream));
+    CU(ev_record(p, p->ev[0]));
     if (p->direction == DFFT_FORWARD) {
         // t0 (+t1): Z pass out of place (bufferDev1 survives), Y pass with the pack (and, P2P, the
         // all-to-all) folded into its store
@@ -907,8 +1013,8 @@ template <typename T> static int execute_fused(dfft_plan p)
                 if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
                 if ((rc = Pass<T>::y_pass(p, p->work, p->work, 0, nullptr))) return rc;
             }
-            CU(cudaEventRecord(p->ev[1], p->stream));
-            CU(cudaEventRecord(p->ev[2], p->stream));
+            CU(ev_record(p, p->ev[1]));
+            CU(ev_record(p, p->ev[2]));
             if (p->natural) { if ((rc = Pass<T>::x_natural(p, p->work, p->buf2))) return rc; }
             else if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
@@ -918,10 +1024,10 @@ template <typename T> static int execute_fused(dfft_plan p)
             if (p->overlap) {
                 if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
                 if ((rc = Pass<T>::fwd_overlapped(p, base))) return rc;
-                CU(cudaEventRecord(p->ev[1], p->stream));
-                CU(cudaEventRecord(p->ev[2], p->stream));
+                CU(ev_record(p, p->ev[1]));
+                CU(ev_record(p, p->ev[2]));
                 if ((rc = flags_signal(p, false, p->epoch))) return rc;
-                CU(cudaEventRecord(p->ev[3], p->stream));
+                CU(ev_record(p, p->ev[3]));
                 p->timed = true;
                 return 0;
             }
@@ -934,9 +1040,9 @@ template <typename T> static int execute_fused(dfft_plan p)
                 if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base))) return rc;
             }
             if ((rc = flags_signal(p, true, p->epoch))) return rc;
-            CU(cudaEventRecord(p->ev[1], p->stream));
+            CU(ev_record(p, p->ev[1]));
             if ((rc = flags_wait(p, true, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
-            CU(cudaEventRecord(p->ev[2], p->stream));
+            CU(ev_record(p, p->ev[2]));
             if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
             if ((rc = flags_signal(p, false, p->epoch))) return rc;
         } else {
@@ -948,19 +1054,19 @@ template <typename T> static int execute_fused(dfft_plan p)
                 if ((rc = Pass<T>::z_pass(p, p->buf1, p->work, false))) return rc;
                 if ((rc = Pass<T>::y_pass(p, p->work, nullptr, 1, base))) return rc;
             }
-            CU(cudaEventRecord(p->ev[1], p->stream));
+            CU(ev_record(p, p->ev[1]));
             if ((rc = nccl_exchange(p, p->buf2, p->work))) return rc;
-            CU(cudaEventRecord(p->ev[2], p->stream));
+            CU(ev_record(p, p->ev[2]));
             if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
         }
-        CU(cudaEventRecord(p->ev[3], p->stream));
+        CU(ev_record(p, p->ev[3]));
     } else {
         const bool scale = (p->flags & DFFT_SCALE_BACKWARD) != 0;
         if (P == 1) {
             if (p->natural) { if ((rc = Pass<T>::x_natural(p, p->buf1, p->buf2))) return rc; }
             else if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
-            CU(cudaEventRecord(p->ev[1], p->stream));
-            CU(cudaEventRecord(p->ev[2], p->stream));
+            CU(ev_record(p, p->ev[1]));
+            CU(ev_record(p, p->ev[2]));
             if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, p->buf2, p->buf2, nullptr, 0, nullptr, scale))) return rc; }
             else if ((rc = Pass<T>::y_pass(p, p->buf2, p->buf2, 0, nullptr))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
@@ -970,9 +1076,9 @@ template <typename T> static int execute_fused(dfft_plan p)
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_BACKWARD), p->esz);
             if ((rc = Pass<T>::x_bwd(p, p->buf1, nullptr, base))) return rc;
             if ((rc = flags_signal(p, true, p->epoch))) return rc;
-            CU(cudaEventRecord(p->ev[1], p->stream));
+            CU(ev_record(p, p->ev[1]));
             if ((rc = flags_wait(p, true, p->epoch))) return rc;
-            CU(cudaEventRecord(p->ev[2], p->stream));
+            CU(ev_record(p, p->ev[2]));
             void* cb[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
             if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale))) return rc; }
@@ -980,16 +1086,16 @@ template <typename T> static int execute_fused(dfft_plan p)
             if ((rc = flags_signal(p, false, p->epoch))) return rc;
         } else {
             if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
-            CU(cudaEventRecord(p->ev[1], p->stream));
+            CU(ev_record(p, p->ev[1]));
             if ((rc = nccl_exchange(p, p->buf2, p->work))) return rc;
-            CU(cudaEventRecord(p->ev[2], p->stream));
+            CU(ev_record(p, p->ev[2]));
             void* cb[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
             if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale))) return rc; }
             else if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
         }
         if (!p->fuse && (rc = Pass<T>::z_pass(p, p->buf2, p->buf2, scale))) return rc;
-        CU(cudaEventRecord(p->ev[3], p->stream));
+        CU(ev_record(p, p->ev[3]));
     }
     p->timed = true;
     return 0;
@@ -1042,7 +1148,7 @@ template <typename T> static int execute_stage(dfft_plan p, int stage)
 
 extern "C" int dfft_execute_stage(dfft_plan p, int stage)
 {
-    if (!p || stage < 0 || stage > 3) return fail(DFFT_EINVAL, "dfft_execute_stage: bad arguments");
+    if (!p || stage < 0 || stage > 3 || p->dry) return fail(DFFT_EINVAL, "dfft_execute_stage: bad arguments");
     if (p->xmode != DFFT_EXCHANGE_STAGED) return fail(DFFT_EINVAL, "dfft_execute_stage needs a plan created with DFFT_EXCHANGE_STAGED");
     CU(cudaSetDevice(p->device));
     return p->prec == DFFT_DOUBLE ? execute_stage<double>(p, stage) : execute_stage<float>(p, stage);
@@ -1051,15 +1157,16 @@ extern "C" int dfft_execute_stage(dfft_plan p, int stage)
 extern "C" int dfft_execute(dfft_plan p)
 {
     if (!p) return fail(DFFT_EINVAL, "null plan");
-    CU(cudaSetDevice(p->device));
+    if (p->dry) p->ops.clear();
+    else CU(cudaSetDevice(p->device));
     if (p->xmode == DFFT_EXCHANGE_STAGED) {
         p->launches = 0;
         for (int s = 0; s < 4; s++) {
-            CU(cudaEventRecord(p->ev[s], p->stream));
+            CU(ev_record(p, p->ev[s]));
             int rc = p->prec == DFFT_DOUBLE ? execute_stage<double>(p, s) : execute_stage<float>(p, s);
             if (rc) return rc;
         }
-        CU(cudaEventRecord(p->ev[4], p->stream));
+        CU(ev_record(p, p->ev[4]));
         p->timed = true;
         return 0;
     }
@@ -1069,6 +1176,7 @@ extern "C" int dfft_execute(dfft_plan p)
 extern "C" int dfft_synchronize(dfft_plan p)
 {
     if (!p) return fail(DFFT_EINVAL, "null plan");
+    if (p->dry) return 0;
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize(p->stream));
     return 0;
@@ -1077,7 +1185,7 @@ extern "C" int dfft_synchronize(dfft_plan p)
 extern "C" int dfft_get_timings(dfft_plan p, double t[5])
 {
     if (!p || !t) return fail(DFFT_EINVAL, "bad arguments");
-    if (!p->timed) return fail(DFFT_EINVAL, "no execute to time yet");
+    if (!p->timed || p->dry) return fail(DFFT_EINVAL, "no execute to time yet");
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize(p->stream));
     float ms[4] = {0, 0, 0, 0};
@@ -1100,7 +1208,7 @@ extern "C" int dfft_get_timings(dfft_plan p, double t[5])
 extern "C" int dfft_get_pass_timings(dfft_plan p, double t[3])
 {
     if (!p || !t) return fail(DFFT_EINVAL, "bad arguments");
-    if (!p->timed) return fail(DFFT_EINVAL, "no execute to time yet");
+    if (!p->timed || p->dry) return fail(DFFT_EINVAL, "no execute to time yet");
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize(p->stream));
     for (int a = 0; a < 3; a++) {
@@ -1113,7 +1221,7 @@ extern "C" int dfft_get_pass_timings(dfft_plan p, double t[3])
 
 extern "C" int dfft_execute_host_async(dfft_plan p, const void* host_in, void* host_out)
 {
-    if (!p || !host_in || !host_out) return fail(DFFT_EINVAL, "bad arguments");
+    if (!p || !host_in || !host_out || p->dry) return fail(DFFT_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaMemcpyAsync(p->buf1, host_in, (size_t)p->in_count * p->esz, cudaMemcpyHostToDevice, p->stream));
     int rc = dfft_execute(p);
@@ -1145,6 +1253,17 @@ extern "C" int dfft_plan_counts(dfft_plan p, long long* ic, long long* oc, long 
     if (mc) *mc = p->max_count;
     return 0;
 }
+/* test hook: JSON array of the passes the last dfft_execute of a DFFT_DRY_RUN plan recorded; returns the length needed */
+extern "C" long long dfft_debug_plan_ops(dfft_plan p, char* buf, long long cap)
+{
+    if (!p) return -1;
+    std::string o = "[";
+    for (size_t i = 0; i < p->ops.size(); i++) { if (i) o += ", "; o += p->ops[i]; }
+    o += "]";
+    if (buf && cap > (long long)o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+    return (long long)o.size() + 1;
+}
+
 extern "C" int dfft_plan_launches(dfft_plan p) { return p ? p->launches : 0; }
 extern "C" int dfft_plan_exchange(dfft_plan p) { return p ? p->xmode : 0; }
 extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? (p->overlap ? 2 : 1) : 0; }
@@ -1181,7 +1300,7 @@ template <typename T> static void upload_lut_e(void** dst, const SizeEntry* e, b
 }
 
 static int make_line_pass(LinePass& lp, int n, long long stride, long long nlines, long long inner, long long inner_dist, long long outer_dist,
-                          int precision)
+                          int precision, bool dry = false)
 {
     const SizeEntry* e = find_size_entry(n, precision);
     if (!e) return fail(DFFT_EUNSUPPORTED, "unsupported length %d", n);
@@ -1201,6 +1320,7 @@ static int make_line_pass(LinePass& lp, int n, long long stride, long long nline
         lp.oa = lp.ia;
         lp.kind = PK_Y;
     }
+    if (dry) return 0;
     if (precision == DFFT_DOUBLE) upload_lut_e<double>(&lp.lut, e, stride == 1);
     else upload_lut_e<float>(&lp.lut, e, stride == 1);
     if (cudaGetLastError() != cudaSuccess || !lp.lut) return fail(DFFT_ECUDA, "twiddle table upload failed");
@@ -1236,7 +1356,7 @@ extern "C" int dfft_lines_destroy(dfft_lines_plan p)
 //   B: FFT along n2 (stride n1) of temp, stored to the caller's buffer at [k2][k1] = natural order X[k1 + n1*k2]
 // -- what the reference does with its multi-upload axes and reorderFourStep = 1 (templateFFT.cpp:4007-4106, 5951).
 // EXPERIMENTAL until it has been run against the oracle on hardware: enabled with DFFT_EXPERIMENTAL_LONG=1.
-static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precision)
+static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precision, bool dry = false)
 {
     long long best1 = 0;
     int best_score = -1;
@@ -1252,7 +1372,8 @@ static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precis
     if (!best1) return fail(DFFT_EUNSUPPORTED, "length %d cannot be split into two supported factors", n);
     const int n1 = (int)best1, n2 = n / n1;
     const size_t esz = precision == DFFT_FLOAT ? 8 : 16;
-    CU(cudaMalloc(&p->temp, (size_t)nlines * n * esz));
+    if (dry) p->temp = fake_addr(0, 4);
+    else CU(cudaMalloc(&p->temp, (size_t)nlines * n * esz));
     // pass A: columns of the [n1][n2] matrix of every line, transposed store + twiddle
     LinePass& a = p->pass[0];
     a.e = find_size_entry(n1, precision);
@@ -1262,7 +1383,8 @@ static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precis
         a.ia = Affine{(long long)n, C, 1, n2};
         a.oa = Affine{(long long)n, (long long)C * n1, n1, 1};
         a.kind = PK_XF_TW; a.tw_n = n; a.src = 0; a.dst = 1;
-        if (precision == DFFT_DOUBLE) upload_lut<double>(&a.lut, a.e->x_nstages, a.e->x_rad);
+        if (dry) {}
+        else if (precision == DFFT_DOUBLE) upload_lut<double>(&a.lut, a.e->x_nstages, a.e->x_rad);
         else upload_lut<float>(&a.lut, a.e->x_nstages, a.e->x_rad);
     }
     // pass B: columns of the [n2][n1] matrix in temp, natural-order result in the caller's buffer
@@ -1274,10 +1396,11 @@ static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precis
         b.ia = Affine{(long long)n, C, 1, n1};
         b.oa = b.ia;
         b.kind = PK_Y; b.src = 1; b.dst = 0;
-        if (precision == DFFT_DOUBLE) upload_lut<double>(&b.lut, b.e->s_nstages, b.e->s_rad);
+        if (dry) {}
+        else if (precision == DFFT_DOUBLE) upload_lut<double>(&b.lut, b.e->s_nstages, b.e->s_rad);
         else upload_lut<float>(&b.lut, b.e->s_nstages, b.e->s_rad);
     }
-    if (cudaGetLastError() != cudaSuccess || !a.lut || !b.lut) return fail(DFFT_ECUDA, "twiddle table upload failed");
+    if (!dry && (cudaGetLastError() != cudaSuccess || !a.lut || !b.lut)) return fail(DFFT_ECUDA, "twiddle table upload failed");
     p->npass = 2;
     p->ordered = true;
     return 0;
@@ -1353,6 +1476,48 @@ extern "C" int dfft_lines_synchronize(dfft_lines_plan p)
 }
 
 extern "C" void* dfft_lines_stream(dfft_lines_plan p) { return p ? (void*)p->stream : nullptr; }
+
+/* test hook (host only): the passes a lines plan would launch for `direction`, as JSON (same format as dfft_debug_plan_ops;
+ * the caller's data is buffer 1 of device 0, the plan's temporary buffer 4); two_d != 0: 2-D plan (n = nx, stride = ny,
+ * nlines = batch).  Long lines always use the four-step plan here.  Returns the bytes needed, < 0 on error. */
+extern "C" long long dfft_debug_lines_ops(int n, long long stride, long long nlines, long long inner, long long inner_dist, long long outer_dist,
+                                          int precision, int direction, int two_d, char* buf, long long cap)
+{
+    dfft_lines_plan_s lp;
+    dfft_plan_s rec;   // only its `ops` vector is used
+    rec.dry = true;
+    lp.prec = precision;
+    int rc = 0;
+    if (two_d) {
+        const int nx = n, ny = (int)stride;
+        const long long batch = nlines;
+        rc = make_line_pass(lp.pass[0], nx, 1, (long long)ny * batch, (long long)ny * batch, nx, 0, precision, true);
+        if (!rc) rc = make_line_pass(lp.pass[1], ny, nx, (long long)nx * batch, nx, 1, (long long)nx * ny, precision, true);
+        lp.npass = 2;
+    } else if (!find_size_entry(n, precision) && stride == 1 && inner_dist == n) {
+        rc = make_four_step(&lp, n, nlines, precision, true);
+    } else {
+        rc = make_line_pass(lp.pass[0], n, stride, nlines, inner, inner_dist, outer_dist, precision, true);
+        lp.npass = 1;
+    }
+    if (rc) return rc;
+    static const char* names[PK_COUNT] = {"Z", "Y", "Y_CO", "Y_CI", "XF", "XB", "XB_CO", "XF_TW"};
+    for (int k = 0; k < lp.npass; k++) {
+        const LinePass& ps = lp.pass[(direction == DFFT_BACKWARD && !lp.ordered) ? lp.npass - 1 - k : k];
+        TileArgs<double> a{};
+        a.in = (const double2*)(ps.src ? lp.temp : fake_addr(0, 1)); a.out = (double2*)(ps.dst ? lp.temp : fake_addr(0, 1));
+        a.ia = ps.ia; a.oa = ps.oa; a.G = ps.G; a.W = ps.W; a.ntiles = ps.ntiles;
+        a.inv = direction == DFFT_BACKWARD; a.tw_n = ps.tw_n;
+        const int C = ps.kind == PK_Z ? ps.e->z_C : (ps.kind == PK_Y ? ps.e->s_C : ps.e->x_C);
+        record_op<double>(&rec, names[ps.kind], k, ps.e->N, C, false, false, ps.kind == PK_XF_TW, a);
+    }
+    lp.temp = nullptr;
+    std::string o = "[";
+    for (size_t i = 0; i < rec.ops.size(); i++) { if (i) o += ", "; o += rec.ops[i]; }
+    o += "]";
+    if (buf && cap > (long long)o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+    return (long long)o.size() + 1;
+}
 
 extern "C" int dfft_fft_lines(void* data, int n, long long stride, long long nlines, long long inner, long long inner_dist,
                               long long outer_dist, int direction, int precision)

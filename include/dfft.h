@@ -54,6 +54,8 @@ extern "C" {
 
 #define DFFT_NATURAL_SPECTRUM 64u /* EXPERIMENTAL, single device: the spectrum (forward output / backward input) is kept in natural
                                     [x][y][z] order instead of the reference's transposed [y][z][x] */
+#define DFFT_DRY_RUN 128u         /* describe-only plan (tests): no CUDA call, `in`/`out` are symbolic addresses, dfft_execute records
+                                    the passes it would launch; read them with dfft_debug_plan_ops.  `comm` may be NULL */
 #define DFFT_OVERLAP_X 32u       /* EXPERIMENTAL (forward, P2P, square planes): the whole transform of a device as one kernel;
                                     the z axis is sent in parts and the X lines of a part start as soon as it has arrived
                                     from every sender, overlapping t3 with the NVLink-bound sends (env DFFT_OVERLAP=1) */
@@ -86,6 +88,14 @@ int dfft_length_schedule(int n, int precision, int* radices, int max_radices);
  * part, plane, tile; returns the number of tickets (ticket < 0: only that) */
 long long dfft_debug_fused3_order(long long planes, long long rows, int GA, int GBk, int GXk, int K, int lag, long long ticket,
                                   long long out[4]);
+/* test hook: JSON description of the passes recorded by the last dfft_execute of a DFFT_DRY_RUN plan (affine maps, chunk
+ * tables, symbolic buffer addresses: device d, buffer b at ((d+1) << 44) | (b << 40), b = 1 bufferDev1, 2 out, 3 receive/work,
+ * 4 intermediate, 5 in).  Returns the number of bytes needed (including the terminator). */
+long long dfft_debug_plan_ops(dfft_plan plan, char* buf, long long cap);
+/* test hook (host only): the passes a lines plan (1-D, 2-D when two_d != 0: n = nx, stride = ny, nlines = batch, or the
+ * four-step plan of a long line) would launch, same JSON as dfft_debug_plan_ops: data = buffer 1, temporary = buffer 4 */
+long long dfft_debug_lines_ops(int n, long long stride, long long nlines, long long inner, long long inner_dist, long long outer_dist,
+                               int precision, int direction, int two_d, char* buf, long long cap);
 /* number of TUNED transform lengths for a precision; fills `lengths` (may be NULL) */
 int dfft_supported_lengths(int precision, int* lengths, int max_lengths);
 
