@@ -52,7 +52,7 @@ extern "C" {
                                     Default: fused when the exchange is P2P (the Y stores are NVLink-bound and hide the
                                     Z role), two sweeps otherwise */
 
-#define DFFT_NATURAL_SPECTRUM 64u /* EXPERIMENTAL, single device: the spectrum (forward output / backward input) is kept in natural
+#define DFFT_NATURAL_SPECTRUM 64u /* single device: the spectrum (forward output / backward input) is kept in natural
                                     [x][y][z] order instead of the reference's transposed [y][z][x] */
 #define DFFT_DRY_RUN 128u         /* describe-only plan (tests): no CUDA call, `in`/`out` are symbolic addresses, dfft_execute records
                                     the passes it would launch; read them with dfft_debug_plan_ops.  `comm` may be NULL */

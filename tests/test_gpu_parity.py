@@ -399,7 +399,6 @@ def test_four_step_long_lines(precision, monkeypatch):
         plan.destroy()
 
 
-@pytest.mark.skipif(os.environ.get("DFFT_TEST_EXPERIMENTAL") != "1", reason="experimental natural-order spectrum: set DFFT_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("n0,n1,n2", [(16, 32, 8), (48, 64, 64), (15, 22, 26)])
 def test_natural_order_spectrum_single_device(n0, n1, n2):
     """DFFT_NATURAL_SPECTRUM: forward output / backward input in natural [x][y][z] order."""
