@@ -571,9 +571,10 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
             }
             __syncthreads();
             OpB::run(B, kb, plane * F.GB + (long long)part * F.GBk + idx, twb);
-            __syncthreads();                                   // every thread's peer stores are issued
+            __threadfence_system();                            // every thread orders its own peer stores at system scope ...
+            __syncthreads();                                   // ... before thread 0 counts the tile
             if (threadIdx.x == 0) {
-                __threadfence_system();                        // ... and ordered (system scope) before the count
+                __threadfence_system();
                 const unsigned long long old = atomicAdd(F.part_done + part, 1ull);
                 if (old + 1 == F.part_target) {                // this tile completes the part on this device
                     __threadfence_system();
