@@ -1,15 +1,21 @@
 #!/bin/bash
-# Sweep of batched 1-D transforms with the surface of templateFFT/batchTest/runTest1D_opt.sh:1-21
-# (powers of 2 from 256, powers of 3, 5, 7; 2^26 points per run, CSV batch_result1D.csv).  Lengths beyond one
-# shared-memory line (6400 points in double) are reported as unsupported and skipped: the reference handles
-# them with multi-upload passes (templateFFT.cpp:4007-4106), this library does not yet.
-DIR="$(cd "$(dirname "$0")" && pwd)"
-num_iter=${NUM_ITER:-1000}
-printResult=0
+# Batched 1-D sweep with the surface of the reference's templateFFT/batchTest/runTest1D_opt.sh (same lengths, same CSV
+# header, 2^26 points per run): geometric ladders of 2 (from 256), 3, 5 and 7 up to the reference's limits.
+# Lengths beyond one shared-memory line (6400 points in double) need DFFT_EXPERIMENTAL_LONG=1 (four-step plan);
+# what is still unsupported is reported and skipped.
+here="$(cd "$(dirname "$0")" && pwd)"
+iters=${NUM_ITER:-1000}
 csv=${CSV:-batch_result1D.csv}
 echo 'X,Y,Z,Buffer,hip_time,GFlops,num_iter,bandwidth,max error' > "$csv"
-run() { "$DIR/batchFFT" 1d "$1" 1 1 "$num_iter" "$printResult" "$csv" || echo "X=$1: skipped (unsupported length)"; }
-for ((X=256; X<=131072; X=X*2)); do run $X; done
-for ((X=3; X<=14348907; X=X*3)); do run $X; done
-for ((X=5; X<=48828125; X=X*5)); do run $X; done
-for ((X=7; X<=40353607; X=X*7)); do run $X; done
+
+ladder() {   # ladder <base> <first> <last>
+  local x=$2
+  while [ "$x" -le "$3" ]; do
+    "$here/batchFFT" 1d "$x" 1 1 "$iters" 0 "$csv" || echo "length $x: skipped (unsupported)"
+    x=$((x * $1))
+  done
+}
+ladder 2 256 131072
+ladder 3 3 14348907
+ladder 5 5 48828125
+ladder 7 7 40353607

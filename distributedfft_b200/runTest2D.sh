@@ -1,13 +1,13 @@
 #!/bin/bash
-# Sweep of batched 2-D transforms with the surface of templateFFT/batchTest/runTest2D_opt.sh:1-12
-# (X, Y from 2048 down to 128; 2^26 points per run, CSV batch_result2D.csv).
-DIR="$(cd "$(dirname "$0")" && pwd)"
-num_iter=${NUM_ITER:-1000}
-printResult=0
+# Batched 2-D sweep with the surface of the reference's templateFFT/batchTest/runTest2D_opt.sh: every (X, Y) pair of
+# {2048, 1024, 512, 256, 128}, 2^26 points per run, same CSV header.
+here="$(cd "$(dirname "$0")" && pwd)"
+iters=${NUM_ITER:-1000}
 csv=${CSV:-batch_result2D.csv}
 echo 'X,Y,Z,Buffer,hip_time,GFlops,num_iter,bandwidth,max error' > "$csv"
-for ((X=2048; X>=128; X=X/2)); do
-  for ((Y=2048; Y>=128; Y=Y/2)); do
-    "$DIR/batchFFT" 2d $X $Y 1 "$num_iter" "$printResult" "$csv" || echo "X=$X Y=$Y: skipped"
+sizes="2048 1024 512 256 128"
+for x in $sizes; do
+  for y in $sizes; do
+    "$here/batchFFT" 2d "$x" "$y" 1 "$iters" 0 "$csv" || echo "${x}x${y}: skipped"
   done
 done
