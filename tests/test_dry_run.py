@@ -264,3 +264,26 @@ def test_lines_plan_schedules_1d_and_2d():
             run_pass(m, op)
         ref = np.fft.fft2(a, axes=(1, 2)) if direction == FORWARD else np.fft.ifft2(a, axes=(1, 2)) * nx * ny
         assert np.abs(m.view(fake(0, BUF1))[0].reshape(a.shape) - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+def test_random_geometries_all_exchanges(co):
+    """Seeded random sweep over device counts, tuned and generic lengths, even and uneven splits, both directions."""
+    rng = np.random.default_rng(2026)
+    lengths = [4, 6, 8, 9, 10, 12, 16, 24, 5, 7, 14, 15, 20, 21, 22, 26, 27, 28, 30, 32]
+    done = 0
+    while done < 24:
+        P = int(rng.integers(1, 7))
+        n0, n1, n2 = (int(x) for x in rng.choice(lengths, 3))
+        g = SlabGeometry(n0, n1, n2, P)
+        if g.last_n0 < 1 or g.last_n1 < 1:
+            continue
+        flags = [dfft.EXCHANGE_P2P, dfft.EXCHANGE_NCCL, dfft.EXCHANGE_P2P | dfft.NO_FUSE][done % 3]
+        direction = FORWARD if done % 2 == 0 else BACKWARD
+        A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+        inputs, ref = oracle(co, g, A, direction)
+        got, names, _ = simulate(n0, n1, n2, P, direction, inputs, flags)
+        scale = max(np.abs(r).max() for r in ref)
+        for d in range(P):
+            n = g.out_count(d) if direction == FORWARD else g.in_count(d)
+            assert np.abs(got[d][:n] - ref[d][:n]).max() <= 1e-11 * scale, (P, n0, n1, n2, flags, direction, d, names[d])
+        done += 1
