@@ -30,6 +30,11 @@ void register_f64(std::vector<SizeEntry>& v)
     using Y512n = Cfg<Sched<512, 8, 8, 8, 8>, 4, false, 3, false>;
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512, Y512, Y512, 1>(3));
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512n, Y512n, Y512n, 1>(4));
+    // DFFT_VARIANT=6|7|8: the contiguous role of the fused kernels synchronises per line (2 warps) instead of per CTA:
+    // default shapes, 3-CTA shapes, 3-CTA shapes + L2 hints
+    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512, Y512, Y512, 2>(6));
+    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512n, Y512n, Y512n, 2>(7));
+    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512n, Y512n, Y512n, 3>(8));
     // DFFT_VARIANT=5: 256-byte rows for the peer (NVLink) stores only; local passes keep the default shapes
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512, Y512, Cfg<Sched<512, 16, 8, 8, 8>, 16, false, 1, false>>(5));
     // mixed radix

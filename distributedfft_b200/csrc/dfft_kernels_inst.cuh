@@ -113,8 +113,9 @@ template <class S_, int C_, bool TW_, int MB_, bool PP_> struct Cfg {
 // Z: contiguous pass.  Y: strided pass on local memory (t0 axis-1, backward unpack).  X: the t3 passes (strided on one
 // side, contiguous on the other).  PEER: the Y pass with the chunked store (pack / peer receive buffers over NVLink),
 // which wants >= 128-byte row segments; must use Y's schedule (it shares the twiddle table).
-// FH = 1: the fused t0 kernels carry L2 eviction hints (first role: streamed input evict_first, intermediate evict_last;
-// second role: intermediate and output evict_first) -- an experiment, see DESIGN.md
+// FH bit 0: the fused t0 kernels carry L2 eviction hints (first role: streamed input evict_first, intermediate evict_last;
+// second role: intermediate and output evict_first); FH bit 1: the contiguous role of the fused kernels synchronises per
+// line (named barriers) instead of per CTA -- experiments, see DESIGN.md
 template <typename T, class Z, class Y, class X = Y, class PEER = Y, int FH = 0>
 SizeEntry make_entry(int variant = 0)
 {
@@ -146,11 +147,13 @@ SizeEntry make_entry(int variant = 0)
     static_assert(NT % ZS::T == 0 && NTP % ZS::T == 0, "strided CTA size must be a multiple of the contiguous line's thread count");
     e.f_zC = NT / ZS::T;
     e.f_zCp = NTP / ZS::T;
-    constexpr int H1 = FH ? 1 : 0, H2 = FH ? 2 : 0;
+    constexpr int H1 = (FH & 1) ? 1 : 0, H2 = (FH & 1) ? 2 : 0;
+    constexpr bool ZL = (FH & 2) != 0 && ZS::T % 32 == 0 && NT / ZS::T <= 15;
+    constexpr bool ZLp = (FH & 2) != 0 && ZS::T % 32 == 0 && NTP / ZS::T <= 15;
     // first-role flavour (intermediate written with evict_last) and second-role flavour (everything evict_first)
-    using OZ = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H2>;
-    using OZ2 = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H1>;
-    using OZp = TileOp<ZS, T, NTP / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H2>;
+    using OZ = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H2, false, ZL>;
+    using OZ2 = TileOp<ZS, T, NT / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H1, false, ZL>;
+    using OZp = TileOp<ZS, T, NTP / ZS::T, MAP_T, MAP_T, false, false, false, false, false, H1, H2, false, ZLp>;
     using OY = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, false, false, false, false, H1, H2>;
     using OY2 = TileOp<SS, T, Y::C, MAP_C, MAP_C, false, false, false, false, false, H1, H1>;
     using OYco = TileOp<SS, T, PEER::C, MAP_C, MAP_C, false, false, true, false, false, H1, 0>;

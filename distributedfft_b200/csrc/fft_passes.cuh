@@ -55,8 +55,17 @@ struct TileSmem {
     static constexpr size_t bytes(bool chunked) { return exch_bytes + lut_bytes + 16 + (chunked ? tab_bytes : 0); }
 };
 
-template <class S, int s, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool PINGPONG>
+// barrier over the threads that share exchange data: the whole CTA, or -- LSYNC, line-major thread map on both sides -- only
+// the S::T threads of one line (named barrier 1 + line), which decouples the lines of a tile from each other
+template <bool LSYNC, int TT> __device__ __forceinline__ void exch_sync(int line)
+{
+    if constexpr (LSYNC) asm volatile("bar.sync %0, %1;" ::"r"(line + 1), "n"(TT) : "memory");
+    else __syncthreads();
+}
+
+template <class S, int s, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool PINGPONG, bool LSYNC = false>
 struct StageRunner {
+    static_assert(!LSYNC || (MAPIN == MAP_T && MAPOUT == MAP_T && S::T % 32 == 0 && C <= 15), "line-level barriers need whole warps per line and at most 15 lines");
     static constexpr int LAST = S::NSTAGES - 1;
     static constexpr int LS = SmemGeom<T>::line(S::N, C);
     // thread (t_in, c_in) for every stage but the last, (t_out, c_out) for the last one
@@ -70,14 +79,14 @@ struct StageRunner {
         if constexpr (s == 0) hook();
         if constexpr (s < LAST) {
             cx<T>* buf = exch + (PINGPONG ? (size_t)pp * C * LS : 0);
-            if constexpr (!PINGPONG) __syncthreads();   // previous readers of the single buffer are done
+            if constexpr (!PINGPONG) exch_sync<LSYNC, S::T>(c_in);   // previous readers of the single buffer are done
             stage_scatter<S, s, T>(v, t_in, buf + c_in * LS);
-            __syncthreads();
+            exch_sync<LSYNC, S::T>(c_in);
             if constexpr (s + 1 == LAST) stage_gather<S, T>(v, t_out, buf + c_out * LS);
             else stage_gather<S, T>(v, t_in, buf + c_in * LS);
             pp ^= 1;
-            StageRunner<S, s + 1, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, exch, pp, lut,
-                                                                    twr + S::tw_regs(s), hook);
+            StageRunner<S, s + 1, T, C, MAPIN, MAPOUT, TWREG, PINGPONG, LSYNC>::run(v, t_in, c_in, t_out, c_out, exch, pp, lut,
+                                                                           twr + S::tw_regs(s), hook);
         }
     }
 };
@@ -171,7 +180,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   [0, exch_bytes) exchange buffer | lut_bytes twiddles | 16 B mbarrier | tab_bytes chunk tables
 // ------------------------------------------------------------------------------------------
 template <class S, typename T, int C, int MAPIN, int MAPOUT, bool TWREG, bool CHUNK_IN, bool CHUNK_OUT, bool PINGPONG, bool PF = false,
-          int HIN = 0, int HOUT = 0, bool EPI = false>
+          int HIN = 0, int HOUT = 0, bool EPI = false, bool LSYNC = false>
 struct TileOp {
     using SM = TileSmem<S, T, C, PINGPONG>;
     static constexpr int R = S::R, TT = S::T, NT = S::T * C;
@@ -304,7 +313,7 @@ struct TileOp {
         }
         // the staging slots are free once the first stage has consumed the registers loaded from them
         auto hook = [&]() { if constexpr (PF) { if (next_tile >= 0) prefetch(A, k, next_tile); } };
-        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG>::run(v, t_in, c_in, t_out, c_out, k.exch, k.pp, k.lut_s, twr, hook);
+        StageRunner<S, 0, T, C, MAPIN, MAPOUT, TWREG, PINGPONG, LSYNC>::run(v, t_in, c_in, t_out, c_out, k.exch, k.pp, k.lut_s, twr, hook);
         if constexpr (EPI) {   // four-step twiddle W_n^(col * k), applied in the forward domain (before the inverse's swap-back)
             const long long col = (long long)b * C + c_out;
 #pragma unroll

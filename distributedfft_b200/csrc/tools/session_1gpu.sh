@@ -7,7 +7,7 @@ T=distributedfft_b200/csrc/tools
 DFFT_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q --durations=8 2>&1 | tail -25 > gpurun_out/s1_pytest.log; tail -6 gpurun_out/s1_pytest.log
 {
   timeout 120 python $T/sweep.py 512:double:0 512:double:0:fuse
-  for v in 1 2 3 4; do timeout 60 python $T/sweep.py 512:double:$v:fuse; done
+  for v in 1 2 3 4 6 7 8; do timeout 60 python $T/sweep.py 512:double:$v:fuse; done
   for lag in 2 4; do DFFT_LAG=$lag timeout 60 python $T/sweep.py 512:double:3:fuse | sed "s/^/lag=$lag /"; done
 } 2>&1 | tee gpurun_out/s1_fused_variants.log
 timeout 300 python bench.py --steps 100 --warmup 5 > gpurun_out/s1_bench.json 2> gpurun_out/s1_bench.err
