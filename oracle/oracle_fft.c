@@ -345,7 +345,15 @@ void oracle_stage_alltoall(cplx **buf2, cplx **buf1, i64 n0, i64 n1, i64 n2, int
             i64 recv_off;
             if (i == P - 1) recv_off = (direction == ORACLE_FORWARD) ? s * xd * lastN1 * n2 : s * lastN0 * yd * n2;
             else recv_off = s * xd * yd * n2;
-            memcpy(buf1[i] + recv_off, buf2[s] + so[i], sizeof(cplx) * (size_t)sc[i]);
+            /* the copy is split over the host threads (a device-to-device copy in the reference); same bytes moved */
+            {
+                cplx *dst = buf1[i] + recv_off;
+                const cplx *src = buf2[s] + so[i];
+                const i64 cnt = sc[i], blk = 1 << 16;
+#pragma omp parallel for schedule(static)
+                for (i64 b0 = 0; b0 < cnt; b0 += blk)
+                    memcpy(dst + b0, src + b0, sizeof(cplx) * (size_t)(cnt - b0 < blk ? cnt - b0 : blk));
+            }
         }
     }
     free(sc);
