@@ -213,12 +213,23 @@ struct dfft_comm_s {
     dfft_allgather_fn ag = nullptr;
     void* ctx = nullptr;
 
-    void barrier()
+    // A participant that fails in the middle of a collective sequence (plan creation) poisons the communicator: every
+    // rank blocked in -- or later entering -- a barrier returns an error instead of waiting for a peer that will never come.
+    bool failed = false;
+    void poison()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        failed = true;
+        cv.notify_all();
+    }
+    int barrier()
     {
         std::unique_lock<std::mutex> lk(mu);
+        if (failed) return -1;
         long long g = gen;
         if (++arrived == nranks) { arrived = 0; gen++; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        else cv.wait(lk, [&] { return gen != g || failed; });
+        return failed ? -1 : 0;
     }
     int allgather(int r, const void* send, void* recv, size_t bytes)
     {
@@ -228,15 +239,15 @@ struct dfft_comm_s {
             std::lock_guard<std::mutex> lk(mu);
             slots[r].assign((const unsigned char*)send, (const unsigned char*)send + bytes);
         }
-        barrier();
+        if (barrier()) return -1;
         for (int i = 0; i < nranks; i++) memcpy((unsigned char*)recv + (size_t)i * bytes, slots[i].data(), bytes);
-        barrier();
+        if (barrier()) return -1;
         return 0;
     }
     int host_barrier(int r)
     {
         if (nranks == 1) return 0;
-        if (local) { barrier(); return 0; }
+        if (local) return barrier();
         std::vector<unsigned char> tmp(nranks);
         unsigned char one = 1;
         return ag(ctx, &one, tmp.data(), 1);
@@ -450,11 +461,12 @@ static void record_op(dfft_plan p, const char* name, int phase, int N, int C, bo
     p->ops.push_back(o);
 }
 
-template <typename T> static void upload_lut(void** dst, int nstages, const int* rad)
+template <typename T> static cudaError_t upload_lut(void** dst, int nstages, const int* rad)
 {
     std::vector<cx<T>> lut = build_lut<T>(nstages, rad);
-    cudaMalloc(dst, lut.size() * sizeof(cx<T>));
-    cudaMemcpy(*dst, lut.data(), lut.size() * sizeof(cx<T>), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMalloc(dst, lut.size() * sizeof(cx<T>));
+    if (e != cudaSuccess) { *dst = nullptr; return e; }
+    return cudaMemcpy(*dst, lut.data(), lut.size() * sizeof(cx<T>), cudaMemcpyHostToDevice);
 }
 
 static int share_pointer(dfft_plan p, void* mine, std::vector<void*>& peers)
@@ -465,7 +477,7 @@ static int share_pointer(dfft_plan p, void* mine, std::vector<void*>& peers)
     if (p->dry) return 0;   // describe-only plans compute peer addresses symbolically
     if (p->comm->local) {
         std::vector<void*> all(P);
-        p->comm->allgather(p->me, &mine, all.data(), sizeof(void*));
+        if (p->comm->allgather(p->me, &mine, all.data(), sizeof(void*)) != 0) return fail(DFFT_ECOMM, "a peer failed during plan creation");
         peers = all;
         return 0;
     }
@@ -483,8 +495,21 @@ static int share_pointer(dfft_plan p, void* mine, std::vector<void*>& peers)
     return 0;
 }
 
+static int plan_create(long long n0, long long n1, long long n2, void* in, void* out, dfft_comm comm, int dev_idx,
+                       int P, int direction, int precision, unsigned flags, dfft_plan* plan_out);
+
 extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* in, void* out, dfft_comm comm, int dev_idx,
                                 int P, int direction, int precision, unsigned flags, dfft_plan* plan_out)
+{
+    const int rc = plan_create(n0, n1, n2, in, out, comm, dev_idx, P, direction, precision, flags, plan_out);
+    // a participant that fails (bad argument, allocation, peer mapping ...) must not leave the others waiting for it
+    // in the collective part of plan creation: the local communicator is poisoned and their barriers return an error
+    if (rc != 0 && P > 1 && comm && comm->local && !(flags & DFFT_DRY_RUN)) comm->poison();
+    return rc;
+}
+
+static int plan_create(long long n0, long long n1, long long n2, void* in, void* out, dfft_comm comm, int dev_idx,
+                       int P, int direction, int precision, unsigned flags, dfft_plan* plan_out)
 {
     if (!plan_out) return fail(DFFT_EINVAL, "null plan pointer");
     *plan_out = nullptr;
@@ -515,7 +540,8 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     p->in = in; p->out = out;
     p->dry = dry;
     int rc = 0;
-    auto bail = [&](int code) { dfft_destroy(p); return code; };
+    // a rank that fails after the collective part has begun must not leave its peers waiting for it
+    auto bail = [&](int code) { if (!dry && P > 1 && comm && comm->local) comm->poison(); dfft_destroy(p); return code; };   // poison BEFORE destroy's barrier
 #define CUP(x)                                                                                        \
     do {                                                                                              \
         cudaError_t e_ = (x);                                                                         \
@@ -539,13 +565,13 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
     if (dry) {
         // no twiddle tables: the interpreter of the recorded passes does its own transforms
     } else if (precision == DFFT_DOUBLE) {
-        upload_lut<double>(&p->lut_z, ez->z_nstages, ez->z_rad);
-        upload_lut<double>(&p->lut_y, ey->s_nstages, ey->s_rad);
-        upload_lut<double>(&p->lut_x, ex->x_nstages, ex->x_rad);
+        CUP(upload_lut<double>(&p->lut_z, ez->z_nstages, ez->z_rad));
+        CUP(upload_lut<double>(&p->lut_y, ey->s_nstages, ey->s_rad));
+        CUP(upload_lut<double>(&p->lut_x, ex->x_nstages, ex->x_rad));
     } else {
-        upload_lut<float>(&p->lut_z, ez->z_nstages, ez->z_rad);
-        upload_lut<float>(&p->lut_y, ey->s_nstages, ey->s_rad);
-        upload_lut<float>(&p->lut_x, ex->x_nstages, ex->x_rad);
+        CUP(upload_lut<float>(&p->lut_z, ez->z_nstages, ez->z_rad));
+        CUP(upload_lut<float>(&p->lut_y, ey->s_nstages, ey->s_rad));
+        CUP(upload_lut<float>(&p->lut_x, ex->x_nstages, ex->x_rad));
     }
     if (!dry) CUP(cudaGetLastError());
     if (flags & DFFT_NATURAL_SPECTRUM) {
@@ -554,9 +580,8 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
         if ((flags & DFFT_EXCHANGE_MASK) == DFFT_EXCHANGE_STAGED) return bail(fail(DFFT_EINVAL, "DFFT_NATURAL_SPECTRUM cannot be combined with the staged mode"));
         p->natural = true;
         if (!dry) {
-            if (precision == DFFT_DOUBLE) upload_lut<double>(&p->lut_xn, ex->s_nstages, ex->s_rad);
-            else upload_lut<float>(&p->lut_xn, ex->s_nstages, ex->s_rad);
-            CUP(cudaGetLastError());
+            if (precision == DFFT_DOUBLE) CUP(upload_lut<double>(&p->lut_xn, ex->s_nstages, ex->s_rad));
+            else CUP(upload_lut<float>(&p->lut_xn, ex->s_nstages, ex->s_rad));
         }
     }
     // exchange mode
@@ -674,7 +699,7 @@ extern "C" int dfft_plan_c2c_3d(long long n0, long long n1, long long n2, void* 
             int r = api.CommInitRank(&p->nccl, P, all[0], p->me);
             if (r != 0) return bail(fail(DFFT_ECOMM, "ncclCommInitRank failed: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
         }
-        comm->host_barrier(p->me);
+        if (comm->host_barrier(p->me) != 0) return bail(fail(DFFT_ECOMM, "a peer failed during plan creation"));
     }
     if (!dry) CUP(cudaDeviceSynchronize());
 #undef CUP
@@ -849,8 +874,10 @@ template <typename T> struct Pass {
         c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
         c.epoch = ++p->overlap_epoch;
         c.part_target = c.epoch * (unsigned long long)(p->n0l * c.GBk);
-        c.my_arrive = &p->sync->part_arrive[0][0];
-        for (int q = 0; q < p->P; q++) c.peer_arrive[q] = &p->peer_sync[q]->part_arrive[0][0];
+        if (!p->dry) {
+            c.my_arrive = &p->sync->part_arrive[0][0];
+            for (int q = 0; q < p->P; q++) c.peer_arrive[q] = &p->peer_sync[q]->part_arrive[0][0];
+        }
         c.lag = p->lag;
         if (p->dry) {
             record_op<T>(p, "ovlZ", 0, e->N, CZ, false, false, false, z);

@@ -1,0 +1,134 @@
+"""CPU test of the NON-dry host control flow of libdfft.so.
+
+Round 1 shipped a library whose every real `dfft_execute` spun forever on the host (a self-recursive event
+helper) while the CPU suite stayed green, because it only ever created DFFT_DRY_RUN plans.  Here the
+library's own object files are linked against tests/fakecuda/fake_cudart.cpp (device memory = host memory,
+launches = counted no-ops) and real plans are driven create -> execute -> timings -> destroy for one
+device and for 2/4 device-threads of a local communicator, in every exchange mode that needs no NCCL,
+under a hard timeout.  A hang, a crash or a bootstrap deadlock fails in seconds, without a GPU."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "distributedfft_b200")
+FAKE_LIB = os.path.join(PKG, "build", "libdfft_fakecuda.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+@pytest.fixture(scope="module")
+def fake_lib():
+    sys.path.insert(0, ROOT)
+    from distributedfft_b200 import build as b
+    b.build()
+    objs = [os.path.join(PKG, "build", s.replace(".cu", ".o")) for s in b.LIB_SOURCES]
+    stub_src = os.path.join(ROOT, "tests", "fakecuda", "fake_cudart.cpp")
+    stub_obj = os.path.join(PKG, "build", "fake_cudart.o")
+    newest = max(os.path.getmtime(p) for p in objs + [stub_src])
+    if not os.path.exists(FAKE_LIB) or os.path.getmtime(FAKE_LIB) < newest:
+        subprocess.run(["g++", "-O1", "-fPIC", "-std=c++17", "-c", stub_src, "-o", stub_obj], check=True)
+        subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "none", "-o", FAKE_LIB] + objs +
+                       [stub_obj, "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"], check=True)
+    return FAKE_LIB
+
+
+WORKER = textwrap.dedent(r'''
+    import ctypes, sys, threading
+    sys.path.insert(0, sys.argv[1])
+    import distributedfft_b200.api as api
+    api.LIB_PATH = sys.argv[2]          # the fake-runtime build of the same objects
+    api._lib = None
+    import distributedfft_b200 as dfft
+    L = dfft.lib()
+    L.fakecuda_launches.restype = ctypes.c_longlong
+    L.fakecuda_event_records.restype = ctypes.c_longlong
+    L.fakecuda_live_allocations.restype = ctypes.c_longlong
+
+    def drive(n0, n1, n2, P, flags, precision=dfft.DOUBLE, executes=3):
+        comm = dfft.LocalComm(P) if P > 1 else None
+        errs, launches = [], [0] * P
+        def worker(p):
+            try:
+                for direction in (dfft.FORWARD, dfft.BACKWARD):
+                    mc = dfft.getMaxDataCount(n0, n1, n2, P, p == P - 1)
+                    a = dfft.fft_mpi_alloc_local_memory(mc, dfft.ALLOC_DEV, precision)
+                    b = dfft.fft_mpi_alloc_local_memory(mc, dfft.ALLOC_DEV, precision)
+                    plan = dfft.fft_mpi_plan_dft_c2c_3d(n0, n1, n2, a, b, comm, p, P, direction, precision, flags)
+                    for _ in range(executes):
+                        plan.execute()
+                    plan.synchronize()
+                    t = plan.timings(); pt = plan.pass_timings()
+                    assert len(t) == 5 and t[4] > 0 and len(pt) == 3
+                    launches[p] += plan.launches
+                    assert plan.launches >= 2
+                    plan.destroy()
+                    L.dfft_free_local(a, dfft.ALLOC_DEV); L.dfft_free_local(b, dfft.ALLOC_DEV)
+            except Exception:
+                import traceback
+                errs.append(traceback.format_exc())
+        if P == 1:
+            worker(0)
+        else:
+            th = [threading.Thread(target=worker, args=(p,)) for p in range(P)]
+            [t.start() for t in th]; [t.join() for t in th]
+        if comm: comm.destroy()
+        assert not errs, "\n".join(errs)
+        return launches
+
+    before = L.fakecuda_launches()
+    for flags in (0, dfft.FORCE_FUSE, dfft.NO_FUSE, dfft.EXCHANGE_STAGED, dfft.SCALE_BACKWARD, dfft.NATURAL_SPECTRUM):
+        drive(64, 64, 64, 1, flags)
+        drive(12, 10, 24, 1, flags, dfft.FLOAT)
+    for P in (2, 4):
+        for flags in (dfft.EXCHANGE_P2P, dfft.EXCHANGE_P2P | dfft.NO_FUSE, dfft.EXCHANGE_P2P | dfft.OVERLAP_X, dfft.EXCHANGE_STAGED):
+            drive(64, 64, 64, P, flags)
+            drive(12, 10, 24, P, flags)          # uneven split (short last slab), generic lengths
+    # the host-buffer entry points and the lines engine
+    cnt = 16 * 16 * 16
+    buf = dfft.fft_mpi_alloc_local_memory(cnt, dfft.ALLOC_DEV)
+    plan = dfft.fft_mpi_plan_dft_c2c_3d(16, 16, 16, buf, None, None, 0, 1, dfft.FORWARD)
+    hin = dfft.fft_mpi_alloc_local_memory(cnt, dfft.ALLOC_CPU); hout = dfft.fft_mpi_alloc_local_memory(cnt, dfft.ALLOC_CPU)
+    plan.execute_host(hin, hout); plan.execute_host_async(hin, hout); plan.synchronize(); plan.destroy()
+    for p_ in (buf,): L.dfft_free_local(p_, dfft.ALLOC_DEV)
+    for p_ in (hin, hout): L.dfft_free_local(p_, dfft.ALLOC_CPU)
+    data = dfft.fft_mpi_alloc_local_memory(4096 * 4, dfft.ALLOC_DEV)
+    dfft.fft_lines(data, 4096, 1, 4, 4, 4096, 4 * 4096, dfft.FORWARD)
+    lp = dfft.LinesPlan(two_d=(64, 32, 2)); lp.execute(data, dfft.FORWARD); lp.execute(data, dfft.BACKWARD); lp.synchronize(); lp.destroy()
+    L.dfft_free_local(data, dfft.ALLOC_DEV)
+    # errors still come back as status codes on the real path
+    try:
+        dfft.fft_mpi_plan_dft_c2c_3d(17, 16, 16, 1, 2, None, 0, 1, dfft.FORWARD)
+        raise SystemExit("unsupported length accepted")
+    except dfft.DfftError:
+        pass
+    # one participant of a collective plan creation fails (null input pointer): its peer must get an error back, not hang
+    comm = dfft.LocalComm(2)
+    out = {}
+    def half(p_):
+        a = dfft.fft_mpi_alloc_local_memory(16 * 16 * 16, dfft.ALLOC_DEV)
+        try:
+            pl = dfft.fft_mpi_plan_dft_c2c_3d(16, 16, 16, a if p_ == 0 else None, None, comm, p_, 2, dfft.FORWARD, dfft.DOUBLE, dfft.EXCHANGE_P2P)
+            pl.destroy(); out[p_] = "created"
+        except dfft.DfftError as e:
+            out[p_] = "error"
+        L.dfft_free_local(a, dfft.ALLOC_DEV)
+    th = [threading.Thread(target=half, args=(k,)) for k in range(2)]
+    [t.start() for t in th]; [t.join(30) for t in th]
+    assert out == {0: "error", 1: "error"}, out
+    comm.destroy()
+    assert L.fakecuda_launches() - before > 100 and L.fakecuda_event_records() > 100
+    assert L.fakecuda_live_allocations() == 0, ("leak", L.fakecuda_live_allocations())
+    print("fakecuda control flow ok: %d launches, %d event records" % (L.fakecuda_launches(), L.fakecuda_event_records()))
+''')
+
+
+def test_non_dry_plans_run_to_completion_on_a_fake_runtime(fake_lib, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, DFFT_VERBOSE="1")
+    r = subprocess.run([sys.executable, str(script), ROOT, fake_lib], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "fakecuda control flow ok" in r.stdout
