@@ -241,6 +241,8 @@ def run_dfft_arm(args):
         flags |= dfft.FORCE_FUSE
     if args.overlap:
         flags |= dfft.OVERLAP_X
+    if args.no_pipeline:
+        flags |= dfft.NO_PIPELINE
     plan = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tin.data_ptr(), tout.data_ptr(), comm, rank, P, dfft.FORWARD, prec, flags)
     stream = torch.cuda.ExternalStream(plan.stream, device=dev)
 
@@ -319,7 +321,13 @@ def run_dfft_arm(args):
     M = float(n) ** 3 / P
     peak, peak_src = measured_peak()
     slab_bytes = 2.0 * esz * M                      # one read + one write of the local slab (per axis pass)
-    if plan.overlapped:
+    if plan.pipeline_parts:
+        # the forward transform of a device is a two-stream pipeline of part kernels (send side: Z, Y parts with the pack and the
+        # peer stores / ncclAlltoAll; receive side: X parts): no single kernel dominates, the roofline is quoted on the whole
+        # transform with SURVEY 8(d)'s algorithmic bytes (6 + 2) * E * M per GPU
+        kernels = [("whole forward transform, stream-pipelined over %d z-parts (send side: Z + Y/pack/exchange parts; receive side: X parts)" % plan.pipeline_parts,
+                    ms_per_step, 4 * slab_bytes, 4 * slab_bytes, "fwd_pipelined")]
+    elif plan.overlapped:
         # the whole forward transform of a device is ONE kernel (Z, Y with peer stores, X behind arrival flags): compulsory
         # HBM traffic = slab read + intermediate write-back + receive-buffer read + result write = 4*E*M
         kernels = [("whole forward transform (fft_fused3_kernel: Z + Y/peer-store + X roles)", passes_avg[0], 2 * slab_bytes, 3 * slab_bytes, "fwd_overlapped")]
@@ -340,7 +348,7 @@ def run_dfft_arm(args):
             traffic = json.load(f).get(f"{n}^3:{args.precision}:P{P}:{kkey}")
     except Exception:
         pass
-    transform_bytes = (6.0 + (2.0 if (P > 1 and plan.exchange == dfft.EXCHANGE_NCCL) else 0.0)) * esz * M
+    transform_bytes = (6.0 + (2.0 if P > 1 else 0.0)) * esz * M   # SURVEY 8(d) / BASELINE.md: (6 + 2*[P>1]) * E * M per GPU
     line = {
         "metric": "3D C2C forward FFT GFlops/s (5*N^3*log2(N^3)/t)", "value": value, "unit": "GFlops/s",
         "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -349,9 +357,10 @@ def run_dfft_arm(args):
         "config": {"workload": f"{n}x{n}x{n} C2C {args.precision} forward, slab decomposition over {P} GPU(s)",
                    "exchange": {1: "p2p-fused", 2: "nccl", 3: "staged"}[plan.exchange] if P > 1 else "none",
                    "l2": "inputs (%.2f GiB per GPU) exceed the 126 MB L2; no flush needed" % (M * esz / 2 ** 30),
-                   "parallelism": f"slab{P}", "t0": "overlapped-single-kernel" if plan.overlapped else ("fused-L2" if plan.fused else "two-sweep")},
+                   "parallelism": f"slab{P}", "pipeline_parts": plan.pipeline_parts, "t0": "overlapped-single-kernel" if plan.overlapped else ("fused-L2" if plan.fused else "two-sweep")},
         "stage_ms": {"t0": stage[0], "t1": stage[1], "t2": stage[2], "t3": stage[3], "total": stage[4]},
-        "pass_ms": ({"forward_single_kernel": passes_avg[0]} if plan.overlapped else {"t0_fused_zy": passes_avg[0], "x": passes_avg[2]} if plan.fused else
+        "pass_ms": ({"send_side_z_y_parts": passes_avg[0], "receive_side_x_parts_span": passes_avg[2]} if plan.pipeline_parts else
+                    {"forward_single_kernel": passes_avg[0]} if plan.overlapped else {"t0_fused_zy": passes_avg[0], "x": passes_avg[2]} if plan.fused else
                     {"z": passes_avg[0], "y": passes_avg[1], "x": passes_avg[2]}),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
@@ -398,6 +407,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large sizes: 4 pinned slabs per rank)")
     ap.add_argument("--no-fuse", action="store_true", help="run t0 as two HBM sweeps (Z pass, Y pass) instead of the fused kernel")
     ap.add_argument("--overlap", action="store_true", help="EXPERIMENTAL: whole forward transform as one kernel, t3 overlapped behind per-part arrivals (P2P, N > 1)")
+    ap.add_argument("--no-pipeline", action="store_true", help="P > 1: disable the stream-pipelined z-part forward path (t2/t3 then run after t0)")
     ap.add_argument("--fuse", action="store_true", help="force the fused L2-resident t0 kernel (default: only with the P2P exchange)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -25,13 +25,14 @@ FORCE_FUSE = 16
 OVERLAP_X = 32
 NATURAL_SPECTRUM = 64
 DRY_RUN = 128
+NO_PIPELINE = 256
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfft.so")
 
 __all__ = [
     "FORWARD", "BACKWARD", "ALLOC_CPU", "ALLOC_DEV", "DOUBLE", "FLOAT", "EXCHANGE_AUTO", "EXCHANGE_P2P",
-    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "OVERLAP_X", "NATURAL_SPECTRUM", "DRY_RUN", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
+    "EXCHANGE_NCCL", "EXCHANGE_STAGED", "SCALE_BACKWARD", "NO_FUSE", "FORCE_FUSE", "OVERLAP_X", "NATURAL_SPECTRUM", "DRY_RUN", "NO_PIPELINE", "DfftError", "lib", "LIB_PATH", "Plan", "LocalComm",
     "BootstrapComm", "fft_mpi_init", "fft_mpi_plan_dft_c2c_3d", "fft_mpi_execute_dft_3d_c2c", "fft_mpi_destroy_plan",
     "fft_mpi_alloc_local_memory", "fft_mpi_local_size_3d", "fft_mpi_cleanup", "getMaxDataCount", "supported_lengths",
     "fft_lines", "lines_ops", "LinesPlan", "length_kind", "length_schedule", "memcpy_htod", "memcpy_dtoh", "exchange_table", "comm_allgather",
@@ -74,7 +75,7 @@ def lib():
     L.dfft_comm_allgather.argtypes = [vp, i, vp, vp, ctypes.c_size_t]
     L.dfft_exchange_table.argtypes = [ll, ll, ll, i, i, i, P(ll), P(ll), P(ll), P(ll)]
     L.dfft_plan_c2c_3d.argtypes = [ll, ll, ll, vp, vp, vp, i, i, i, i, u, P(vp)]
-    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused"):
+    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused", "dfft_plan_pipeline_parts"):
         getattr(L, name).argtypes = [vp]
     L.dfft_execute_stage.argtypes = [vp, i]
     L.dfft_execute_host.argtypes = [vp, vp, vp]
@@ -279,6 +280,11 @@ class Plan:
         buf = ctypes.create_string_buffer(int(n))
         lib().dfft_debug_plan_ops(self.handle, buf, n)
         return json.loads(buf.value.decode())
+
+    @property
+    def pipeline_parts(self):
+        """z-parts of the stream-pipelined forward path (0 = not pipelined)"""
+        return lib().dfft_plan_pipeline_parts(self.handle)
 
     @property
     def overlapped(self):

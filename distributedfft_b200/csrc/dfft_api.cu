@@ -427,12 +427,23 @@ struct dfft_plan_s {
     void* mid = nullptr;
     unsigned long long* part_done = nullptr;
     unsigned long long overlap_epoch = 0;
+    // stream-pipelined forward (DFFT_PIPELINE): the z axis is cut into `parts`; the send side (stream: Z, then the Y pass of
+    // part k with the pack / peer stores folded in, or + ncclAlltoAll of part k on the comm stream) runs ahead of the receive
+    // side (stream2: X pass of part k as soon as part k has arrived from every sender) -- t2 and t3 overlap t0
+    bool pipe = false;
+    bool in_pipe = false;            // inside fwd_pipelined: Pass::launch leaves the per-pass event brackets alone
+    cudaStream_t stream2 = nullptr, stream3 = nullptr;   // receive side; NCCL part exchanges
+    cudaEvent_t ev_join = nullptr, evb[2] = {nullptr, nullptr};
+    cudaEvent_t ev_y[DFFT_MAX_PARTS] = {}, ev_a[DFFT_MAX_PARTS] = {};
+    void* sendbuf = nullptr;         // NCCL: part-major packed send buffer
 };
 
 // symbolic device address of a describe-only plan: device d (0-based), buffer id b: 1 bufferDev1, 2 bufferDev2 / user out,
 // 3 work / receive buffer, 4 intermediate of the single-kernel path, 5 user in
 static inline void* fake_addr(int d, int b) { return (void*)((((unsigned long long)(d + 1)) << 44) | (((unsigned long long)b) << 40)); }
 static inline cudaError_t ev_record(dfft_plan p, cudaEvent_t e) { return p->dry ? cudaSuccess : cudaEventRecord(e, p->stream); }
+static inline cudaError_t ev_record_on(dfft_plan p, cudaEvent_t e, cudaStream_t st) { return p->dry ? cudaSuccess : cudaEventRecord(e, st); }
+static inline cudaError_t stream_wait(dfft_plan p, cudaStream_t st, cudaEvent_t e) { return p->dry ? cudaSuccess : cudaStreamWaitEvent(st, e, 0); }
 
 template <typename T>
 static void record_op(dfft_plan p, const char* name, int phase, int N, int C, bool chunk_in, bool chunk_out, bool transposed_store, const TileArgs<T>& a)
@@ -669,6 +680,46 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
             }
         }
     }
+    {
+        // stream-pipelined forward (z-parts): send side and receive side on two streams, see fwd_pipelined
+        const char* env = getenv("DFFT_PIPELINE");
+        bool want = P > 1 && direction == DFFT_FORWARD && !p->overlap && (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_NCCL);
+        if (env) want = want && strcmp(env, "0") != 0;
+        if (flags & DFFT_NO_PIPELINE) want = false;
+        if (xmode == DFFT_EXCHANGE_NCCL && (n0 % P || n1 % P)) want = false;   // ncclAlltoAll parts need equal chunks
+        if (want) {
+            const int cy = ey->p_C, cx_ = ex->x_C;
+            const int m = cy > cx_ ? cy : cx_;
+            int K = 0;
+            if (m % cy == 0 && m % cx_ == 0) {
+                for (int k : {4, 2})
+                    if (n2 % ((long long)k * m) == 0 && n2 / k >= 32) { K = k; break; }
+                if (getenv("DFFT_PARTS")) {
+                    const int k = atoi(getenv("DFFT_PARTS"));
+                    if (k >= 1 && k <= DFFT_MAX_PARTS && n2 % ((long long)k * m) == 0) K = k;
+                }
+            }
+            if (K >= 1 && (K > 1 || getenv("DFFT_PARTS"))) {
+                p->parts = K;
+                p->pipe = true;
+                if (dry) { p->mid = fake_addr(dev_idx, 4); p->sendbuf = fake_addr(dev_idx, 6); }
+                else {
+                    if (!p->mid) CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
+                    if (xmode == DFFT_EXCHANGE_NCCL) {
+                        CUP(cudaMalloc(&p->sendbuf, (size_t)p->max_count * p->esz));
+                        CUP(cudaStreamCreateWithFlags(&p->stream3, cudaStreamNonBlocking));
+                    }
+                    CUP(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+                    CUP(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+                    for (auto& e : p->evb) CUP(cudaEventCreate(&e));
+                    for (int k = 0; k < K; k++) {
+                        CUP(cudaEventCreateWithFlags(&p->ev_y[k], cudaEventDisableTiming));
+                        CUP(cudaEventCreateWithFlags(&p->ev_a[k], cudaEventDisableTiming));
+                    }
+                }
+            }
+        }
+    }
     if (P > 1 && dry) {
         p->peer_work.resize(P);
         for (int q = 0; q < P; q++) p->peer_work[q] = fake_addr(q, 3);
@@ -720,7 +771,16 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->buf1) cudaFree(p->buf1);
     if (p->work) cudaFree(p->work);
     if (p->sync) cudaFree(p->sync);
+    if (p->stream2) cudaStreamSynchronize(p->stream2);
+    if (p->stream3) cudaStreamSynchronize(p->stream3);
     if (p->mid) cudaFree(p->mid);
+    if (p->sendbuf) cudaFree(p->sendbuf);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    for (auto& e : p->evb) if (e) cudaEventDestroy(e);
+    for (auto& e : p->ev_y) if (e) cudaEventDestroy(e);
+    for (auto& e : p->ev_a) if (e) cudaEventDestroy(e);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
+    if (p->stream3) cudaStreamDestroy(p->stream3);
     if (p->part_done) cudaFree(p->part_done);
     if (p->plane_done) cudaFree(p->plane_done);
     if (p->ticket) cudaFree(p->ticket);
@@ -748,8 +808,9 @@ extern "C" int dfft_memcpy(void* dst, const void* src, size_t bytes, int kind)
 // pass launches
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Pass {
-    static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a, int axis_override = -1)
+    static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a, int axis_override = -1, cudaStream_t st = nullptr)
     {
+        if (!st) st = p->stream;
         a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
         a.gen = e->gen;
         const int axis = axis_override >= 0 ? axis_override : (kind == PK_Z ? 0 : (kind == PK_Y || kind == PK_Y_CO || kind == PK_Y_CI ? 1 : 2));
@@ -763,9 +824,9 @@ template <typename T> struct Pass {
             p->launches++;
             return 0;
         }
-        ev_record(p, p->pev[axis][0]);
-        cudaError_t err = e->launch[kind](&a, p->sms, p->stream);
-        ev_record(p, p->pev[axis][1]);
+        if (!p->in_pipe) ev_record(p, p->pev[axis][0]);
+        cudaError_t err = e->launch[kind](&a, p->sms, st);
+        if (!p->in_pipe) ev_record(p, p->pev[axis][1]);
         if (err != cudaSuccess) return fail(DFFT_ECUDA, "pass launch (kind %d, N=%d) failed: %s", kind, e->N, cudaGetErrorString(err));
         p->launches++;
         return 0;
@@ -917,6 +978,68 @@ template <typename T> struct Pass {
         a.oa = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
         return launch(p, p->ex, PK_XF, a);
     }
+    // ---- z-part variants (stream-pipelined forward): part k of K covers the columns z in [k*zk, (k+1)*zk) ----------
+    // Y pass of one z-part: mid[x_l][y][z in part] -> chunk q (the rows of destination device q) at chunk_base[q], laid out
+    // [x_l][y_l(q)][z'] with row length zk: the part-major receive (P2P) / send (NCCL) layout
+    static void y_part_args(dfft_plan p, TileArgs<T>& a, const void* src, long long zk, int k, void* const* chunk_base, int C)
+    {
+        const Geom& g = p->g;
+        a.in = (const cx<T>*)src + k * zk; a.out = nullptr; a.lut = (const cx<T>*)p->lut_y;
+        a.G = (int)cdiv(zk, C); a.W = (int)zk; a.ntiles = p->n0l * a.G;
+        a.ia = Affine{g.n1 * g.n2, C, 1, g.n2};
+        a.oa = Affine{0, C, 1, zk};
+        a.co.ediv = (int)g.yd(); a.co.nchunks = p->P;
+        for (int q = 0; q < p->P; q++) { a.co.cptr[q] = chunk_base[q]; a.co.SAq[q] = g.n1l(q) * zk; }
+    }
+    static int y_part(dfft_plan p, const void* src, long long zk, int k, void* const* chunk_base, int cap)
+    {
+        TileArgs<T> a{};
+        y_part_args(p, a, src, zk, k, chunk_base, p->ey->p_C);
+        a.max_ctas_per_sm = cap;
+        return launch(p, p->ey, PK_Y_CO, a);
+    }
+    // part 0 together with the Z pass of every plane in one persistent kernel (fft_fused2_kernel): Z: src -> mid (L2),
+    // Y part 0: mid -> chunks
+    static int zy_fused_part0(dfft_plan p, const void* src, void* mid, long long zk, void* const* chunk_base)
+    {
+        const Geom& g = p->g;
+        const SizeEntry* e = p->ez;
+        TileArgs<T> z{}, y{};
+        const int CZ = e->f_zCp, CY = e->p_C;
+        z.lut = (const cx<T>*)p->lut_z;
+        z.G = (int)cdiv(g.n1, CZ); z.W = (int)g.n1; z.ntiles = p->n0l * z.G;
+        z.ia = Affine{g.n1 * g.n2, (long long)CZ * g.n2, g.n2, 1}; z.oa = z.ia;
+        z.in = (const cx<T>*)src; z.out = (cx<T>*)mid;
+        y_part_args(p, y, mid, zk, 0, chunk_base, CY);
+        FusedCtl c{};
+        c.plane_done = p->plane_done; c.ticket = p->ticket; c.planes = p->n0l;
+        c.GA = z.G; c.GB = y.G;
+        c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
+        c.lag = p->lag;
+        if (p->dry) {
+            record_op<T>(p, "fusedZ", 0, e->N, CZ, false, false, false, z);
+            record_op<T>(p, "fusedY", 0, e->N, CY, false, true, false, y);
+            p->launches++;
+            return 0;
+        }
+        cudaError_t err = e->fused[FK_ZY_CO](&z, &y, &c, p->sms, p->stream);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "fused t0 (part 0) launch (N=%d) failed: %s", e->N, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
+    }
+    // X pass of one z-part on the receive side: rpart = [x (all N0)][y_l][z'] (row length zk) -> dst[y_l][z in part][x]
+    static int x_part(dfft_plan p, const void* rpart, void* dst, long long zk, int k, int cap, cudaStream_t st)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ex->x_C;
+        a.in = (const cx<T>*)rpart; a.out = (cx<T>*)dst + k * zk * g.n0; a.lut = (const cx<T>*)p->lut_x;
+        a.G = (int)cdiv(zk, C); a.W = (int)zk; a.ntiles = p->n1l * a.G;
+        a.ia = Affine{zk, C, 1, p->n1l * zk};
+        a.oa = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
+        a.max_ctas_per_sm = cap;
+        return launch(p, p->ex, PK_XF, a, -1, st);
+    }
     // backward X: src = [y_l][z][x] -> dst = [x][y_l][z] (chunked by destination device when chunk_base)
     static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base)
     {
@@ -967,20 +1090,25 @@ extern "C" int dfft_exchange_table(long long n0, long long n1, long long n2, int
     return 0;
 }
 
-static int flags_signal(dfft_plan p, bool arrive, unsigned long long value)
+// which: 0 = ready[], 1 = arrive[], 2 + k = part_arrive[k][]
+static int flags_signal(dfft_plan p, int which, unsigned long long value, cudaStream_t st = nullptr)
 {
     if (p->dry) return 0;
     FlagPtrs fp{};
-    for (int q = 0; q < p->P; q++) fp.p[q] = arrive ? &p->peer_sync[q]->arrive[p->me] : &p->peer_sync[q]->ready[p->me];
-    signal_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, p->stream>>>(fp, p->P, value);
+    for (int q = 0; q < p->P; q++) {
+        SyncBlock* sb = p->peer_sync[q];
+        fp.p[q] = which == 1 ? &sb->arrive[p->me] : (which == 0 ? &sb->ready[p->me] : &sb->part_arrive[which - 2][p->me]);
+    }
+    signal_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, st ? st : p->stream>>>(fp, p->P, value);
     CU(cudaGetLastError());
     p->launches++;
     return 0;
 }
-static int flags_wait(dfft_plan p, bool arrive, unsigned long long value)
+static int flags_wait(dfft_plan p, int which, unsigned long long value, cudaStream_t st = nullptr)
 {
     if (value == 0 || p->dry) return 0;
-    wait_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, p->stream>>>(arrive ? p->sync->arrive : p->sync->ready, p->P, value);
+    const unsigned long long* f = which == 1 ? p->sync->arrive : (which == 0 ? p->sync->ready : p->sync->part_arrive[which - 2]);
+    wait_flags_kernel<<<1, DFFT_MAX_CHUNKS, 0, st ? st : p->stream>>>(f, p->P, value);
     CU(cudaGetLastError());
     p->launches++;
     return 0;
@@ -1023,6 +1151,111 @@ static int nccl_exchange(dfft_plan p, const void* sendbuf, void* recvbuf)
     return 0;
 }
 
+// one z-part of the all-to-all in NCCL mode (even split): `count` elements to / from every device, chunk q of the send
+// part at q*count, the chunk received from device s at s*count of the receive part
+static int nccl_exchange_part(dfft_plan p, const void* sendpart, void* recvpart, long long count, cudaStream_t st)
+{
+    if (p->dry) {
+        char buf[160];
+        std::string o = "{\"op\": \"alltoall\", \"phase\": 0, ";
+        snprintf(buf, sizeof(buf), "\"send\": %llu, \"recv\": %llu, \"esz\": %zu, \"chunks\": [", (unsigned long long)(size_t)sendpart,
+                 (unsigned long long)(size_t)recvpart, p->esz);
+        o += buf;
+        for (int q = 0; q < p->P; q++) {
+            snprintf(buf, sizeof(buf), "%s[%d, %lld, %lld, %lld]", q ? ", " : "", q, (long long)q * count, (long long)p->me * count, count);
+            o += buf;
+        }
+        o += "]}";
+        p->ops.push_back(o);
+        p->launches++;
+        return 0;
+    }
+    NcclApi& api = nccl_api();
+    if (api.AlltoAll && !getenv("DFFT_NCCL_SENDRECV")) {
+        NC(api.AlltoAll(sendpart, recvpart, (size_t)count * p->esz, /*ncclInt8*/ 0, p->nccl, st));
+    } else {
+        NC(api.GroupStart());
+        for (int q = 0; q < p->P; q++) {
+            NC(api.Send(eoff((void*)sendpart, (long long)q * count, p->esz), (size_t)count * p->esz, 0, q, p->nccl, st));
+            NC(api.Recv(eoff(recvpart, (long long)q * count, p->esz), (size_t)count * p->esz, 0, q, p->nccl, st));
+        }
+        NC(api.GroupEnd());
+    }
+    p->launches++;
+    return 0;
+}
+
+// Stream-pipelined forward transform (P > 1).  The reference runs t0, t1, t2, t3 back to back with a device-wide sync
+// after each (fft_mpi_3d_api.cpp:181-201, 610-672: no overlap at all).  Here the z axis is cut into K parts:
+//   send side, plan stream    : Z pass of the slab (fused with Y part 0 through L2 when the planes are square), then for
+//                               every part k the Y pass of its columns, whose store IS the pack (t1) and -- P2P -- the
+//                               all-to-all (t2): rows go straight into the peers' receive buffers over NVLink, followed by a
+//                               per-part arrival flag.  NCCL: the packed part is handed to ncclAlltoAll on the comm stream.
+//   receive side, second stream: as soon as part k has arrived from every sender, the X pass of the (y_l, z in part k)
+//                               lines (t3, unpack + transpose folded into its load / store), while later parts are still
+//                               being computed and sent.
+// Both sides cap their resident CTAs per SM while they overlap so that they co-reside on every SM.
+// Receive / send buffers are part-major: part k of device q = [x (all N0)][y_l][z'] with z' < zk at k * N0 * n1_l(q) * zk.
+template <typename T> static int fwd_pipelined(dfft_plan p)
+{
+    const Geom& g = p->g;
+    const int P = p->P, me = p->me, K = p->parts;
+    const long long zk = g.n2 / K;
+    const bool p2p = p->xmode == DFFT_EXCHANGE_P2P;
+    cudaStream_t A = p->stream, B = p->stream2, Cs = p->stream3;
+    int rc = 0;
+    struct Guard { dfft_plan p; ~Guard() { p->in_pipe = false; } } guard{p};
+    p->in_pipe = true;
+    int cap = 1;
+    if (getenv("DFFT_PIPE_CAP")) cap = atoi(getenv("DFFT_PIPE_CAP"));
+    if (p2p) {
+        p->epoch++;
+        if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
+    }
+    CU(ev_record(p, p->pev[0][0]));
+    for (int k = 0; k < K; k++) {
+        void* base[DFFT_MAX_CHUNKS];
+        for (int q = 0; q < P; q++)
+            base[q] = p2p ? eoff(p->peer_work[q], ((long long)k * g.n0 + (long long)me * g.xd()) * g.n1l(q) * zk, p->esz)
+                          : eoff(p->sendbuf, ((long long)k * P + q) * p->n0l * g.yd() * zk, p->esz);
+        if (k == 0 && p->fuse) rc = Pass<T>::zy_fused_part0(p, p->buf1, p->mid, zk, base);
+        else {
+            if (k == 0 && (rc = Pass<T>::z_pass(p, p->buf1, p->mid, false))) return rc;
+            rc = Pass<T>::y_part(p, p->mid, zk, k, base, k > 0 ? cap : 0);
+        }
+        if (rc) return rc;
+        if (p2p) {
+            if ((rc = flags_signal(p, 2 + k, p->epoch, A))) return rc;
+        } else {
+            const long long chunk = p->n0l * g.yd() * zk;
+            CU(ev_record_on(p, p->ev_y[k], A));
+            CU(stream_wait(p, Cs, p->ev_y[k]));
+            if ((rc = nccl_exchange_part(p, eoff(p->sendbuf, (long long)k * P * chunk, p->esz), eoff(p->work, (long long)k * P * chunk, p->esz), chunk, Cs))) return rc;
+            CU(ev_record_on(p, p->ev_a[k], Cs));
+        }
+    }
+    CU(ev_record(p, p->pev[0][1]));
+    CU(ev_record(p, p->pev[1][0]));
+    CU(ev_record(p, p->pev[1][1]));
+    CU(ev_record(p, p->ev[1]));
+    for (int k = 0; k < K; k++) {
+        if (p2p) { if ((rc = flags_wait(p, 2 + k, p->epoch, B))) return rc; }
+        else CU(stream_wait(p, B, p->ev_a[k]));
+        if (k == 0) CU(ev_record_on(p, p->pev[2][0], B));
+        if (k == K - 1) CU(ev_record_on(p, p->evb[0], B));
+        if ((rc = Pass<T>::x_part(p, eoff(p->work, (long long)k * g.n0 * p->n1l * zk, p->esz), p->buf2, zk, k, k < K - 1 ? cap : 0, B))) return rc;
+    }
+    CU(ev_record_on(p, p->pev[2][1], B));
+    CU(ev_record_on(p, p->evb[1], B));
+    if (p2p && (rc = flags_signal(p, 0, p->epoch, B))) return rc;
+    CU(ev_record_on(p, p->ev_join, B));
+    CU(stream_wait(p, A, p->ev_join));
+    CU(ev_record(p, p->ev[2]));
+    CU(ev_record(p, p->ev[3]));
+    p->timed = true;
+    return 0;
+}
+
 template <typename T> static int execute_fused(dfft_plan p)
 {
     const Geom& g = p->g;
@@ -1030,6 +1263,7 @@ template <typename T> static int execute_fused(dfft_plan p)
     int rc;
     p->launches = 0;
     CU(ev_record(p, p->ev[0]));
+    if (p->pipe) return fwd_pipelined<T>(p);
     if (p->direction == DFFT_FORWARD) {
         // t0 (+t1): Z pass out of place (bufferDev1 survives), Y pass with the pack (and, P2P, the
         // all-to-all) folded into its store
@@ -1049,29 +1283,29 @@ template <typename T> static int execute_fused(dfft_plan p)
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_FORWARD), p->esz);
             p->epoch++;
             if (p->overlap) {
-                if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
+                if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
                 if ((rc = Pass<T>::fwd_overlapped(p, base))) return rc;
                 CU(ev_record(p, p->ev[1]));
                 CU(ev_record(p, p->ev[2]));
-                if ((rc = flags_signal(p, false, p->epoch))) return rc;
+                if ((rc = flags_signal(p, 0, p->epoch))) return rc;
                 CU(ev_record(p, p->ev[3]));
                 p->timed = true;
                 return 0;
             }
             if (p->fuse) {
-                if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
+                if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
                 if ((rc = Pass<T>::zy_fused(p, p->buf1, p->buf2, nullptr, 1, base, false))) return rc;
             } else {
                 if ((rc = Pass<T>::z_pass(p, p->buf1, p->buf2, false))) return rc;
-                if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;
+                if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;
                 if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base))) return rc;
             }
-            if ((rc = flags_signal(p, true, p->epoch))) return rc;
+            if ((rc = flags_signal(p, 1, p->epoch))) return rc;
             CU(ev_record(p, p->ev[1]));
-            if ((rc = flags_wait(p, true, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
+            if ((rc = flags_wait(p, 1, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
             CU(ev_record(p, p->ev[2]));
             if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
-            if ((rc = flags_signal(p, false, p->epoch))) return rc;
+            if ((rc = flags_signal(p, 0, p->epoch))) return rc;
         } else {
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->buf2, send_off(g, me, q, DFFT_FORWARD), p->esz);
@@ -1098,19 +1332,19 @@ template <typename T> static int execute_fused(dfft_plan p)
             else if ((rc = Pass<T>::y_pass(p, p->buf2, p->buf2, 0, nullptr))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
             p->epoch++;
-            if ((rc = flags_wait(p, false, p->epoch - 1))) return rc;
+            if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_BACKWARD), p->esz);
             if ((rc = Pass<T>::x_bwd(p, p->buf1, nullptr, base))) return rc;
-            if ((rc = flags_signal(p, true, p->epoch))) return rc;
+            if ((rc = flags_signal(p, 1, p->epoch))) return rc;
             CU(ev_record(p, p->ev[1]));
-            if ((rc = flags_wait(p, true, p->epoch))) return rc;
+            if ((rc = flags_wait(p, 1, p->epoch))) return rc;
             CU(ev_record(p, p->ev[2]));
             void* cb[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
             if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale))) return rc; }
             else if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
-            if ((rc = flags_signal(p, false, p->epoch))) return rc;
+            if ((rc = flags_signal(p, 0, p->epoch))) return rc;
         } else {
             if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
             CU(ev_record(p, p->ev[1]));
@@ -1220,6 +1454,15 @@ extern "C" int dfft_get_timings(dfft_plan p, double t[5])
         for (int s = 0; s < 4; s++) CU(cudaEventElapsedTime(&ms[s], p->ev[s], p->ev[s + 1]));
         if (p->direction == DFFT_BACKWARD) { std::swap(ms[0], ms[3]); std::swap(ms[1], ms[2]); }
         for (int s = 0; s < 4; s++) t[s] = ms[s];
+    } else if (p->pipe) {
+        // send side [start, last part issued] = t0 (+t1, + the sends); exposed exchange = from there until the last part has
+        // arrived from every sender; t3 = the X pass of the last part (the earlier parts ran under t0)
+        float a, b, c;
+        CU(cudaEventElapsedTime(&a, p->ev[0], p->ev[1]));
+        CU(cudaEventElapsedTime(&b, p->ev[1], p->evb[0]));
+        CU(cudaEventElapsedTime(&c, p->evb[0], p->evb[1]));
+        if (b < 0) { c += b; b = 0; }
+        t[0] = a; t[1] = 0; t[2] = b; t[3] = c;
     } else {
         float a, b, c;
         CU(cudaEventElapsedTime(&a, p->ev[0], p->ev[1]));
@@ -1293,6 +1536,7 @@ extern "C" long long dfft_debug_plan_ops(dfft_plan p, char* buf, long long cap)
 
 extern "C" int dfft_plan_launches(dfft_plan p) { return p ? p->launches : 0; }
 extern "C" int dfft_plan_exchange(dfft_plan p) { return p ? p->xmode : 0; }
+extern "C" int dfft_plan_pipeline_parts(dfft_plan p) { return p && p->pipe ? p->parts : 0; }
 extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? (p->overlap ? 2 : 1) : 0; }
 extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }
 

@@ -67,6 +67,7 @@ static cudaError_t launch_generic(const void* vargs, int sm_count, cudaStream_t 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GEN_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (a.max_ctas_per_sm > 0 && occ > a.max_ctas_per_sm) occ = a.max_ctas_per_sm;
     long long grid = (long long)sm_count * occ;
     if (grid > a.ntiles) grid = a.ntiles;
     kern<<<(unsigned)grid, GEN_THREADS, smem, st>>>(a, g);

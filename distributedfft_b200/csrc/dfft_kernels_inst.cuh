@@ -27,6 +27,7 @@ cudaError_t launch_pass(const void* vargs, int sm_count, cudaStream_t st)
         occ_cache[dev & 63].store(occ);
     }
     if (a.ntiles <= 0) return cudaSuccess;
+    if (a.max_ctas_per_sm > 0 && occ > a.max_ctas_per_sm) occ = a.max_ctas_per_sm;
     long long grid = (long long)sm_count * occ;
     if (grid > a.ntiles) grid = a.ntiles;
     kern<<<(unsigned)grid, S::T * C, smem, st>>>(a);

@@ -44,6 +44,8 @@ template <typename T> struct TileArgs {
     ChunkTab ci, co;       // used when CHUNK_IN / CHUNK_OUT
     const void* gen;       // host pointer to the GenSched of a generic-length entry (read by its launcher only)
     long long tw_n;        // four-step epilogue (EPI): multiply output (column col, point k) by e^{-2 pi i col*k / tw_n}; 0 = off
+    int max_ctas_per_sm;   // launcher only: cap on resident CTAs per SM (0 = occupancy limit); the stream-pipelined forward path
+                           // leaves SM slots free so that the send-side Y parts and the receive-side X parts co-reside
 };
 
 template <class S, typename T, int C, bool PINGPONG>

@@ -60,6 +60,12 @@ extern "C" {
                                     the z axis is sent in parts and the X lines of a part start as soon as it has arrived
                                     from every sender, overlapping t3 with the NVLink-bound sends (env DFFT_OVERLAP=1) */
 
+#define DFFT_NO_PIPELINE 256u     /* forward, P > 1: do NOT cut the z axis into parts.  Default (P2P and NCCL exchanges): the send
+                                    side (Z, then per part the Y pass + pack + peer stores / ncclAlltoAll) and the receive side
+                                    (X pass of a part once it has arrived from every sender) run on two streams, so t2 and t3
+                                    overlap t0 -- the reference has no overlap at all (fft_mpi_3d_api.cpp:610-672).
+                                    env DFFT_PIPELINE=0 also disables it, DFFT_PARTS=k picks the number of parts */
+
 #define DFFT_EINVAL (-1)
 #define DFFT_ECUDA (-2)
 #define DFFT_EUNSUPPORTED (-3)
@@ -168,6 +174,8 @@ int dfft_plan_launches(dfft_plan plan);
 /* 2: forward transform runs as the single overlapped kernel (DFFT_OVERLAP_X); 1: t0 runs as the fused two-pass
  * kernel (square planes, N1 == N2); 0: separate passes */
 int dfft_plan_fused(dfft_plan plan);
+/* number of z-parts of the stream-pipelined forward path, 0 when the plan does not use it */
+int dfft_plan_pipeline_parts(dfft_plan plan);
 /* which exchange the plan resolved to (DFFT_EXCHANGE_*) */
 int dfft_plan_exchange(dfft_plan plan);
 /* the stream the plan launches on (a cudaStream_t), so callers can time with events on it */

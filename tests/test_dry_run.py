@@ -188,6 +188,42 @@ def test_single_kernel_forward_schedule(co, P, n):
         assert np.abs(got[d][: g.out_count(d)] - ref[d][: g.out_count(d)]).max() <= 1e-11 * scale
 
 
+PIPE_SHAPES = [("p2p", 2, 8, 128, 128, None), ("p2p", 4, 8, 12, 128, None), ("p2p", 3, 10, 9, 128, None), ("p2p", 8, 16, 64, 64, "2"),
+               ("p2p", 2, 6, 64, 64, "1"), ("nccl", 2, 8, 16, 128, None), ("nccl", 4, 8, 8, 64, "2"), ("nccl", 8, 64, 64, 64, "4")]
+
+
+@pytest.mark.parametrize("mode,P,n0,n1,n2,parts", PIPE_SHAPES)
+def test_stream_pipelined_forward_schedule(co, monkeypatch, mode, P, n0, n1, n2, parts):
+    """The z-part pipeline (fwd_pipelined): Z, Y parts with part-major peer stores / packed send parts + per-part
+    all-to-all, X parts reading the part-major receive buffer -- reproduces the reference's forward result for even
+    and uneven splits, fused (square planes) and two-sweep t0, P2P and NCCL exchanges."""
+    if parts:
+        monkeypatch.setenv("DFFT_PARTS", parts)
+    g = SlabGeometry(n0, n1, n2, P)
+    rng = np.random.default_rng(P + n2)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    inputs, ref = oracle(co, g, A, FORWARD)
+    flags = dfft.EXCHANGE_P2P if mode == "p2p" else dfft.EXCHANGE_NCCL
+    got, names, fused = simulate(n0, n1, n2, P, FORWARD, inputs, flags)
+    K = int(parts) if parts else 4
+    for d in range(P):
+        assert names[d].count("XF") == K, names[d]
+        if mode == "nccl":
+            assert names[d].count("alltoall") == K and names[d][0] == "Z"
+        elif n1 == n2 and dfft.length_kind(n1) == 2:
+            assert names[d][:2] == ["fusedZ", "fusedY"] and names[d].count("Y_CO") == K - 1
+        else:
+            assert names[d][0] == "Z" and names[d].count("Y_CO") == K
+    scale = max(np.abs(r).max() for r in ref)
+    for d in range(P):
+        assert np.abs(got[d][: g.out_count(d)] - ref[d][: g.out_count(d)]).max() <= 1e-11 * scale, d
+    # DFFT_NO_PIPELINE falls back to the single-part schedule
+    got2, names2, _ = simulate(n0, n1, n2, P, FORWARD, inputs, flags | dfft.NO_PIPELINE)
+    assert names2[0].count("XF") == 1
+    for d in range(P):
+        assert np.abs(got2[d][: g.out_count(d)] - ref[d][: g.out_count(d)]).max() <= 1e-11 * scale, d
+
+
 @pytest.mark.parametrize("n0,n1,n2", [(8, 16, 4), (12, 10, 24), (15, 22, 26)])
 def test_natural_spectrum_schedule(n0, n1, n2):
     rng = np.random.default_rng(n0)
