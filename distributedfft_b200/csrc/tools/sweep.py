@@ -2,7 +2,7 @@
 """Developer tool: time forward transforms for several (size, precision, DFFT_VARIANT, flags) in one process.
 Single GPU:   python sweep.py 512:double:0 512:double:1 ...
 Multi GPU:    torchrun --nproc-per-node P sweep.py ...     (P2P exchange, process per GPU)
-An item is  size:precision:variant[:fuse|nofuse]"""
+An item is  size:precision:variant[:fuse|nofuse|nopipe|nccl|...][;ENV=value;ENV=value...]   (flags joined with '+')"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", ".."))
 import torch
@@ -21,12 +21,23 @@ if world > 1:
         return out
     comm = dfft.BootstrapComm(rank, world, ag)
 
+FLAGS = {"fuse": dfft.FORCE_FUSE, "nofuse": dfft.NO_FUSE, "nopipe": dfft.NO_PIPELINE, "nccl": dfft.EXCHANGE_NCCL, "p2p": dfft.EXCHANGE_P2P,
+         "overlap": dfft.OVERLAP_X, "": 0}
+SWEEP_ENV = set()
 for item in sys.argv[1:]:
-    parts = item.split(":")
+    head, *envs = item.split(";")
+    for k in SWEEP_ENV:
+        os.environ.pop(k, None)
+    for kv in envs:
+        k, v = kv.split("=")
+        os.environ[k] = v
+        SWEEP_ENV.add(k)
+    parts = head.split(":")
     n, precs, var = int(parts[0]), parts[1], parts[2]
     flags = 0
     if len(parts) > 3:
-        flags = {"fuse": dfft.FORCE_FUSE, "nofuse": dfft.NO_FUSE}[parts[3]]
+        for f in parts[3].split("+"):
+            flags |= FLAGS[f]
     os.environ["DFFT_VARIANT"] = var
     prec = dfft.DOUBLE if precs == "double" else dfft.FLOAT
     tdt = torch.complex128 if prec == dfft.DOUBLE else torch.complex64
@@ -56,7 +67,7 @@ for item in sys.argv[1:]:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, pt, st = t[0].item(), t[1:4].tolist(), t[4:].tolist()
     if rank == 0:
-        print(f"{item:28s} P={world} fused={int(plan.fused)} ms/step {ms:8.4f}  pass {[round(x, 4) for x in pt]}  stage {[round(x, 4) for x in st[:4]]}", flush=True)
+        print(f"{item:60s} P={world} fused={int(plan.fused)} parts={plan.pipeline_parts} ms/step {ms:8.4f}  pass {[round(x, 4) for x in pt]}  stage {[round(x, 4) for x in st[:4]]}", flush=True)
     plan.destroy()
     del tin, tout
     torch.cuda.empty_cache()

@@ -276,3 +276,86 @@ def minstd_uniform(count: int, state: int = 4242):
         s = (s * a) % m; hi = s - 1
         out[j] = (lo + hi * R) / (R * R)
     return out, s
+
+
+# ------------------------------------------------------------------------------------------
+# oracle/_ref: the reference tree's own heFFTe 2.1.0 (stock CPU backend), compiled from the sources under
+# /root/reference by oracle/ref_heffte/Makefile -- the EXECUTED reference that pins the restatements above
+# and the `--impl reference` CPU arm of bench.py.  The .so is git-ignored and travels to the GPU box prebuilt.
+# ------------------------------------------------------------------------------------------
+_REF_DIR = os.path.join(_HERE, "_ref")
+_REF_LIB = os.path.join(_REF_DIR, "libheffte_ref.so")
+_REF_SRC = "/root/reference/heffte/heffteBenchmark"
+
+
+def build_ref(force: bool = False):
+    """Build oracle/_ref/libheffte_ref.so when the reference tree is present (this container); on the GPU box the
+    prebuilt file is used as is.  Returns its path, or None when it neither exists nor can be built."""
+    rdir = os.path.join(_HERE, "ref_heffte")
+    if os.path.isdir(_REF_SRC):
+        deps = [os.path.join(rdir, f) for f in ("heffte_ref.cpp", "tmpi.cpp", "mpi.h", "heffte_config.h", "Makefile")]
+        if force or not os.path.exists(_REF_LIB) or os.path.getmtime(_REF_LIB) < max(os.path.getmtime(d) for d in deps):
+            subprocess.run(["make", "-C", rdir, "-s", f"REF={_REF_SRC}"], check=True)
+    return _REF_LIB if os.path.exists(_REF_LIB) else None
+
+
+class HeffteRef:
+    """ctypes binding of oracle/_ref/libheffte_ref.so (oracle/ref_heffte/heffte_ref.cpp): world-array transforms by the
+    reference tree's heFFTe over P slab ranks (threads behind the mpi.h stand-in)."""
+    ALGORITHMS = {"alltoallv": 0, "alltoall": 1, "p2p_plined": 2, "p2p": 3}
+
+    def __init__(self):
+        path = build_ref()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libheffte_ref.so is missing and /root/reference is not available to build it")
+        self.lib = ctypes.CDLL(path)
+        vp, i = ctypes.c_void_p, ctypes.c_int
+        self.lib.heffte_ref_fft3d_c2c.argtypes = [i, i, i, i, vp, vp, i, i, i, i]
+        self.lib.heffte_ref_time.argtypes = [i, i, i, i, i, i, i, i, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+
+    def version(self):
+        return int(self.lib.heffte_ref_version())
+
+    def pin_ranks(self, cpus):
+        """pin rank i to cpus[i % len(cpus)] (one CPU per physical core, see physical_core_cpus()); [] clears it"""
+        arr = (ctypes.c_int * max(1, len(cpus)))(*cpus)
+        self.lib.tmpi_set_cpus(arr, len(cpus))
+
+    def fft3d(self, A: np.ndarray, P: int, direction: int = FORWARD, algorithm: str = "p2p_plined", scale_full: bool = False) -> np.ndarray:
+        """A[x][y][z] (complex128 / complex64) -> its forward (direction +1) or backward spectrum, natural order"""
+        prec = 0 if A.dtype == np.complex128 else 1
+        A = np.ascontiguousarray(A)
+        out = np.zeros_like(A)
+        n0, n1, n2 = A.shape
+        rc = self.lib.heffte_ref_fft3d_c2c(n0, n1, n2, P, A.ctypes.data, out.ctypes.data, direction, self.ALGORITHMS[algorithm], prec, int(scale_full))
+        if rc != 0:
+            raise ValueError(f"heffte_ref_fft3d_c2c failed ({rc})")
+        return out
+
+    def time_forward(self, n0, n1, n2, P, reps=3, warmup=1, algorithm="p2p_plined", precision=0, pair_reps=0):
+        """returns (forward seconds per repetition, speed3d-protocol seconds = mean of (forward + backward) / 2)"""
+        t = (ctypes.c_double * reps)()
+        pair = ctypes.c_double(0)
+        rc = self.lib.heffte_ref_time(n0, n1, n2, P, reps, warmup, pair_reps, self.ALGORITHMS[algorithm], precision, t, ctypes.byref(pair))
+        if rc != 0:
+            raise ValueError(f"heffte_ref_time failed ({rc})")
+        return list(t), float(pair.value)
+
+
+def physical_core_cpus():
+    """One logical CPU per physical core among the CPUs this process may run on (hyperthread siblings dropped)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        allowed = list(range(os.cpu_count() or 1))
+    seen, out = set(), []
+    for c in allowed:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                key = f.read().strip()
+        except OSError:
+            key = str(c)
+        if key not in seen:
+            seen.add(key)
+            out.append(c)
+    return out
