@@ -8,8 +8,11 @@ A "step" is one forward transform of the synthetic N^3 cube (BASELINE.json confi
 1 GPU; the same cube sharded over N GPUs = strong scaling).  N > 1 runs one process per GPU under
 torchrun; torch.distributed is plumbing only (bootstrap of IPC handles, barrier, max-over-ranks).
 
-`--impl reference` times the CPU oracle port of the reference path (oracle/oracle_fft.c, OpenMP on all
-host cores): the reference's own implementation needs HIP/rocFFT/MPI and cannot be built here.
+`--impl reference` times the reference tree's own CPU FFT on the host cores: heFFTe 2.1.0 with its `stock` backend
+(oracle/_ref/libheffte_ref.so, built from /root/reference/heffte/heffteBenchmark by oracle/ref_heffte/Makefile; slab
+decomposition, p2p_plined reshape like heffteSpeed.sh), one rank per physical core, ranks pinned.  The reference's GPU hot
+path (3dmpifft_opt) needs HIP/hiprtc/rocFFT/MPI and cannot be built here.  If the prebuilt library is missing the
+arm falls back to the OpenMP oracle port (oracle/oracle_fft.c) and says so (`kind: "port"`).
 """
 from __future__ import annotations
 
@@ -24,6 +27,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# CPU legs: threads bound to cores, one per place (must be set before the first OpenMP runtime starts)
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
 
 
 def flops(n0, n1, n2):
@@ -150,22 +156,64 @@ def cpu_forward_rate(n, budget_s=20.0, steps=None, warmup=0):
     return {"best_s": best, "mean_s": mean, "threads": threads, "sample": sample, "scale": scale, "times": times}
 
 
+def ref_forward_rate(n, steps, warmup, budget_s, precision="double"):
+    """Times forward transforms of the n^3 cube by the reference tree's heFFTe (stock backend) over one slab rank per
+    physical core (oracle/_ref).  `steps` timed transforms when they fit `budget_s`, fewer otherwise (said in `sample`).
+    Returns None when oracle/_ref/libheffte_ref.so is absent."""
+    from oracle import HeffteRef, build_ref, physical_core_cpus
+    if build_ref() is None:
+        return None
+    ref = HeffteRef()
+    cpus = physical_core_cpus()
+    P = max(1, min(len(cpus), n))
+    ref.pin_ranks(cpus)
+    prec = 0 if precision == "double" else 1
+    probe, _ = ref.time_forward(n, n, n, P, reps=1, warmup=0, algorithm="p2p_plined", precision=prec)
+    per = 2.0 * probe[0] + 1e-4                        # every timed forward is followed by an untimed backward
+    reps = max(1, min(steps, int(budget_s / per) - warmup))
+    wu = max(0, min(warmup, int(budget_s / per) - reps))
+    times, pair = ref.time_forward(n, n, n, P, reps=reps, warmup=wu, algorithm="p2p_plined", precision=prec, pair_reps=min(2, reps))
+    sample = (f"{reps} full {n}^3 forward transforms by heFFTe {ref.version()} stock backend (AVX2), slab decomposition over {P} ranks "
+              f"(threads behind oracle/ref_heffte/mpi.h, pinned one per physical core), reshape p2p_plined"
+              + ("" if reps == steps else f"; {steps} steps requested, bounded to {reps} by the {budget_s:.0f} s budget")
+              + f"; speed3d protocol (mean of forward+backward)/2 = {pair * 1e3:.1f} ms")
+    return {"best_s": min(times), "mean_s": sum(times) / len(times), "threads": P, "sample": sample, "times": times, "kind": "reference",
+            "logical_cpus": os.cpu_count()}
+
+
+def scipy_forward_rate(n, workers, reps=3):
+    """scipy.fft.fftn (pocketfft, complex128) with all cores, best of `reps` warm runs."""
+    import numpy as np
+    import scipy.fft
+    rng = np.random.default_rng(4242)
+    a = rng.random((n, n, n)) + 0j
+    scipy.fft.fftn(a, workers=workers)
+    best = 1e30
+    for _ in range(reps):
+        t = time.perf_counter(); scipy.fft.fftn(a, workers=workers); best = min(best, time.perf_counter() - t)
+    return best
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     n = args.size
-    r = cpu_forward_rate(n, budget_s=20.0, steps=args.steps, warmup=args.warmup)
+    r = ref_forward_rate(n, args.steps, args.warmup, budget_s=150.0, precision=args.precision)
+    arm = "the reference tree's own CPU FFT: heFFTe 2.1.0 stock backend (oracle/_ref, built from /root/reference/heffte/heffteBenchmark)"
+    if r is None:
+        r = cpu_forward_rate(n, budget_s=20.0, steps=args.steps, warmup=args.warmup)
+        r["kind"] = "port"
+        arm = "CPU oracle port of the reference path (oracle/oracle_fft.c, OpenMP): oracle/_ref/libheffte_ref.so is missing"
     ms = r["mean_s"] * 1e3
     val = flops(n, n, n) * 1e-9 / r["mean_s"]
     line = {
         "impl": "reference", "metric": "3D C2C forward FFT GFlops/s (5*N^3*log2(N^3)/t)", "value": val, "unit": "GFlops/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n}x{n}x{n} C2C double forward, slab decomposition over {args.gpus} GPU(s)",
-                   "arm": "CPU oracle port of the reference path (oracle/oracle_fft.c, OpenMP; the reference itself needs HIP/rocFFT/MPI)",
-                   "host_threads": r["threads"], "exchange": "none (one process)", "parallelism": "cpu"},
-        "cpu_baseline": {"value": val, "unit": "GFlops/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.precision == "double" else "f32", "data": "synthetic",
+        "config": {"workload": f"{n}x{n}x{n} C2C {args.precision} forward, slab decomposition over {args.gpus} GPU(s)",
+                   "arm": arm, "host_threads": r["threads"], "exchange": "in-process (ranks are threads)", "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "GFlops/s", "cores": r["threads"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": val, "unit": "GFlops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -374,10 +422,25 @@ def run_dfft_arm(args):
         "clocks": clocks,
     }
     if P == 1 and rank == 0 and not args.no_cpu:
-        n_cpu = n
-        r = cpu_forward_rate(n_cpu, budget_s=15.0)
-        line["cpu_baseline"] = {"value": flops(n_cpu, n_cpu, n_cpu) * 1e-9 / r["best_s"], "unit": "GFlops/s", "cores": r["threads"],
-                                "kind": "port", "sample": r["sample"]}
+        # reported baseline (not the target): the reference tree's heFFTe on the host cores, bounded to ~20 s; beside it the
+        # OpenMP oracle port and scipy's pocketfft, a few seconds each
+        r = ref_forward_rate(n, steps=5, warmup=1, budget_s=20.0, precision=args.precision)
+        kind = "reference"
+        if r is None:
+            r = cpu_forward_rate(n, budget_s=15.0)
+            kind = "port"
+        line["cpu_baseline"] = {"value": F * 1e-9 / r["best_s"], "unit": "GFlops/s", "cores": r["threads"], "kind": kind, "sample": r["sample"]}
+        others = {}
+        try:
+            if kind == "reference":
+                rp = cpu_forward_rate(n, budget_s=6.0)
+                others["oracle_port_openmp"] = {"value": F * 1e-9 / rp["best_s"], "threads": rp["threads"], "sample": rp["sample"]}
+            from oracle import physical_core_cpus
+            w = len(physical_core_cpus())
+            others["scipy_fft_fftn"] = {"value": F * 1e-9 / scipy_forward_rate(n, w, reps=2), "workers": w, "sample": f"scipy.fft.fftn complex128 {n}^3, best of 2 warm runs"}
+        except Exception as exc:   # the extra legs never take the bench line down
+            others["error"] = repr(exc)
+        line["cpu_baseline"]["other_cpu_ffts"] = others
     if rank == 0:
         print(json.dumps(line))
     for h_in, h_out in hbuf:

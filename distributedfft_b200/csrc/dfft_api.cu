@@ -436,6 +436,7 @@ struct dfft_plan_s {
     cudaEvent_t ev_join = nullptr, evb[2] = {nullptr, nullptr};
     cudaEvent_t ev_y[DFFT_MAX_PARTS] = {}, ev_a[DFFT_MAX_PARTS] = {};
     void* sendbuf = nullptr;         // NCCL: part-major packed send buffer
+    unsigned int* done_ctr = nullptr; // [DFFT_MAX_PARTS] finished-CTA counters of the part kernels (arrival signal folded into the kernel)
 };
 
 // symbolic device address of a describe-only plan: device d (0-based), buffer id b: 1 bufferDev1, 2 bufferDev2 / user out,
@@ -709,6 +710,10 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
                         CUP(cudaMalloc(&p->sendbuf, (size_t)p->max_count * p->esz));
                         CUP(cudaStreamCreateWithFlags(&p->stream3, cudaStreamNonBlocking));
                     }
+                    if (xmode == DFFT_EXCHANGE_P2P && !getenv("DFFT_SIGNAL_KERNELS")) {
+                        CUP(cudaMalloc((void**)&p->done_ctr, DFFT_MAX_PARTS * sizeof(unsigned int)));
+                        CUP(cudaMemset(p->done_ctr, 0, DFFT_MAX_PARTS * sizeof(unsigned int)));
+                    }
                     CUP(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
                     CUP(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
                     for (auto& e : p->evb) CUP(cudaEventCreate(&e));
@@ -775,6 +780,7 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->stream3) cudaStreamSynchronize(p->stream3);
     if (p->mid) cudaFree(p->mid);
     if (p->sendbuf) cudaFree(p->sendbuf);
+    if (p->done_ctr) cudaFree(p->done_ctr);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (auto& e : p->evb) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_y) if (e) cudaEventDestroy(e);
@@ -990,6 +996,11 @@ template <typename T> struct Pass {
         a.oa = Affine{0, C, 1, zk};
         a.co.ediv = (int)g.yd(); a.co.nchunks = p->P;
         for (int q = 0; q < p->P; q++) { a.co.cptr[q] = chunk_base[q]; a.co.SAq[q] = g.n1l(q) * zk; }
+        if (p->xmode == DFFT_EXCHANGE_P2P && !p->dry && p->done_ctr) {
+            // the kernel's last CTA publishes "part k of sender me has arrived" (epoch) on every receiving device
+            a.sig_n = p->P; a.sig_val = p->epoch; a.done_ctr = p->done_ctr + k;
+            for (int q = 0; q < p->P; q++) a.sig[q] = &p->peer_sync[q]->part_arrive[k][p->me];
+        }
     }
     static int y_part(dfft_plan p, const void* src, long long zk, int k, void* const* chunk_base, int cap)
     {
@@ -1225,7 +1236,7 @@ template <typename T> static int fwd_pipelined(dfft_plan p)
         }
         if (rc) return rc;
         if (p2p) {
-            if ((rc = flags_signal(p, 2 + k, p->epoch, A))) return rc;
+            if (!p->done_ctr && (rc = flags_signal(p, 2 + k, p->epoch, A))) return rc;   // else folded into the part kernel
         } else {
             const long long chunk = p->n0l * g.yd() * zk;
             CU(ev_record_on(p, p->ev_y[k], A));

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fft_generic_kernel(const TileArgs
             st_stream(p, v);
         }
     }
+    signal_when_grid_done<T>(A);
 }
 
 }  // namespace dfft

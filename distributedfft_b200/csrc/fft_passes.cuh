@@ -44,6 +44,13 @@ template <typename T> struct TileArgs {
     ChunkTab ci, co;       // used when CHUNK_IN / CHUNK_OUT
     const void* gen;       // host pointer to the GenSched of a generic-length entry (read by its launcher only)
     long long tw_n;        // four-step epilogue (EPI): multiply output (column col, point k) by e^{-2 pi i col*k / tw_n}; 0 = off
+    // completion signal folded into the kernel (stream-pipelined forward): when sig_n > 0 the last CTA to finish publishes
+    // sig_val at sig[0..sig_n) -- the per-part arrival flags on the receiving devices, peer-mapped -- with system-scope release
+    // semantics after every CTA's (peer) stores; done_ctr counts finished CTAs and is re-armed by that last CTA
+    unsigned long long* sig[DFFT_MAX_CHUNKS];
+    unsigned long long sig_val;
+    unsigned int* done_ctr;
+    int sig_n;
     int max_ctas_per_sm;   // launcher only: cap on resident CTAs per SM (0 = occupancy limit); the stream-pipelined forward path
                            // leaves SM slots free so that the send-side Y parts and the receive-side X parts co-reside
 };
@@ -159,6 +166,26 @@ template <int H, typename C_> __device__ __forceinline__ void st_pol(C_* p, C_ v
 {
     if constexpr (H == 0) st_stream(p, v);
     else st_hint(p, v, pol);
+}
+
+// Called by every thread of a CTA after its last store.  Orders the CTA's (peer) stores at system scope, counts the CTA and --
+// in the last CTA of the grid -- publishes the value at the flag addresses.  Receivers poll with ld.acquire.sys.
+template <typename T>
+__device__ __forceinline__ void signal_when_grid_done(const TileArgs<T>& A)
+{
+    if (A.sig_n <= 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned prev = atomicAdd(A.done_ctr, 1u);
+        if (prev == gridDim.x - 1) {
+            *A.done_ctr = 0;
+            __threadfence_system();
+            for (int q = 0; q < A.sig_n; q++)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.sig[q]), "l"(A.sig_val) : "memory");
+        }
+    }
 }
 
 // per-thread asynchronous global -> shared copies (LDGSTS): the next tile's elements are fetched into the
@@ -367,6 +394,7 @@ __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<
         const long long next = tile + gridDim.x;
         Op::run(A, k, tile, twr, next < A.ntiles ? next : -1);
     }
+    signal_when_grid_done<T>(A);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -448,9 +476,18 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
             OpB::run(B, kb, plane * F.GB + idx, twb);
         }
     }
+    if (B.sig_n > 0) { __threadfence_system(); __syncthreads(); }   // this CTA's (peer) stores are ordered before it is counted
     if (threadIdx.x == 0) {
+        if (B.sig_n > 0) __threadfence_system();
         const unsigned left = atomicAdd(F.ticket + 1, 1u);
-        if (left == gridDim.x - 1) { F.ticket[0] = 0; F.ticket[1] = 0; __threadfence(); }
+        if (left == gridDim.x - 1) {
+            F.ticket[0] = 0; F.ticket[1] = 0; __threadfence();
+            if (B.sig_n > 0) {   // last CTA: every Y tile of the part is stored -> publish the arrival flags
+                __threadfence_system();
+                for (int q = 0; q < B.sig_n; q++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(B.sig[q]), "l"(B.sig_val) : "memory");
+            }
+        }
     }
 }
 
