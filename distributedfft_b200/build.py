@@ -41,8 +41,16 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build(force: bool = False, tools: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, tools: bool = False, verbose: bool = False, experiments: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
+    common = COMMON + (["-DDFFT_EXPERIMENTS"] if experiments else [])
+    stamp = os.path.join(BUILD, "experiments.stamp")
+    if experiments != os.path.exists(stamp):   # switching the flavour rebuilds everything
+        force = True
+        if experiments:
+            open(stamp, "w").close()
+        elif os.path.exists(stamp):
+            os.remove(stamp)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     jobs = []
     objs = []
@@ -51,7 +59,7 @@ def build(force: bool = False, tools: bool = False, verbose: bool = False) -> st
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            jobs.append([NVCC] + ARCH + COMMON + ["-c", s, "-o", o])
+            jobs.append([NVCC] + ARCH + common + ["-c", s, "-o", o])
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
             for out in ex.map(_run, jobs):
@@ -77,5 +85,5 @@ def build(force: bool = False, tools: bool = False, verbose: bool = False) -> st
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, tools="--tools" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv, tools="--tools" in sys.argv, verbose=True, experiments="--experiments" in sys.argv)
     print("built", LIB)

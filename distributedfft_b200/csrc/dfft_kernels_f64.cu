@@ -19,6 +19,8 @@ void register_f64(std::vector<SizeEntry>& v)
                            Cfg<Sched<1024, 16, 16, 8, 8>, 8, false, 1, false>, Cfg<Sched<1024, 16, 16, 8, 8>, 8, false, 1, false>>());
     v.push_back(make_entry<T, Cfg<Sched<2048, 16, 16, 16, 8>, 1, false, 4, false>, Cfg<Sched<2048, 16, 16, 16, 8>, 4, false, 1, false>>());
     v.push_back(make_entry<T, Cfg<Sched<4096, 16, 16, 16, 16>, 1, false, 2, false>, Cfg<Sched<4096, 16, 16, 16, 16>, 2, false, 1, false>>());
+#ifdef DFFT_EXPERIMENTS   // build with -DDFFT_EXPERIMENTS (python -m distributedfft_b200.build --experiments): alternate tunings selected
+                          // at run time with DFFT_VARIANT=n; the default library ships only configurations that passed parity on hardware
     // experiments for the fused t0 kernel (DFFT_VARIANT=1|2, not used by default): the strided role reads its tile from L2,
     // not HBM, so narrow tiles (64- / 32-byte rows) cost no DRAM efficiency there and allow 3-5 smaller CTAs per SM
     // (finer-grained phases; the fused kernel's top stall is the CTA barrier, profiles/r1_ncu_full_fused_t0_512.txt)
@@ -35,8 +37,10 @@ void register_f64(std::vector<SizeEntry>& v)
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512, Y512, Y512, 2>(6));
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512n, Y512n, Y512n, 2>(7));
     v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512n, Y512n, Y512n, 3>(8));
+#endif
+    using Y512d = Cfg<Sched<512, 16, 8, 8, 8>, 8, false, 2, false>;
     // DFFT_VARIANT=5: 256-byte rows for the peer (NVLink) stores only; local passes keep the default shapes
-    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512, Y512, Cfg<Sched<512, 16, 8, 8, 8>, 16, false, 1, false>>(5));
+    v.push_back(make_entry<T, Cfg<Sched<512, 8, 8, 8, 8>, 2, true, 4, true>, Y512d, Y512d, Cfg<Sched<512, 16, 8, 8, 8>, 16, false, 1, false>>(5));
     // mixed radix
     // 768 (kbench5): 24 points/thread (8.8.4.3, three exchanges instead of four): Z 2.83 vs 3.45 ms, Y 3.87 vs 4.28, X 3.52 vs 4.19
     v.push_back(make_entry<T, Cfg<Sched<768, 24, 8, 8, 4, 3>, 4, false, 2, false>, Cfg<Sched<768, 24, 8, 8, 4, 3>, 4, false, 2, false>>());
