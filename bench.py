@@ -27,6 +27,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the CPUs this process may use, taken BEFORE any OpenMP runtime (torch's) binds the main thread to one core
+try:
+    CPUS_ALLOWED = sorted(os.sched_getaffinity(0))
+except AttributeError:
+    CPUS_ALLOWED = list(range(os.cpu_count() or 1))
 # CPU legs: threads bound to cores, one per place (must be set before the first OpenMP runtime starts)
 os.environ.setdefault("OMP_PROC_BIND", "close")
 os.environ.setdefault("OMP_PLACES", "cores")
@@ -164,7 +169,7 @@ def ref_forward_rate(n, steps, warmup, budget_s, precision="double"):
     if build_ref() is None:
         return None
     ref = HeffteRef()
-    cpus = physical_core_cpus()
+    cpus = physical_core_cpus(CPUS_ALLOWED)
     P = max(1, min(len(cpus), n))
     ref.pin_ranks(cpus)
     prec = 0 if precision == "double" else 1
@@ -187,6 +192,10 @@ def scipy_forward_rate(n, workers, reps=3):
     import scipy.fft
     rng = np.random.default_rng(4242)
     a = rng.random((n, n, n)) + 0j
+    try:   # pocketfft's worker threads inherit the caller's mask: undo an OpenMP runtime's binding of the main thread
+        os.sched_setaffinity(0, CPUS_ALLOWED)
+    except (AttributeError, OSError):
+        pass
     scipy.fft.fftn(a, workers=workers)
     best = 1e30
     for _ in range(reps):
@@ -436,7 +445,7 @@ def run_dfft_arm(args):
                 rp = cpu_forward_rate(n, budget_s=6.0)
                 others["oracle_port_openmp"] = {"value": F * 1e-9 / rp["best_s"], "threads": rp["threads"], "sample": rp["sample"]}
             from oracle import physical_core_cpus
-            w = len(physical_core_cpus())
+            w = len(physical_core_cpus(CPUS_ALLOWED))
             others["scipy_fft_fftn"] = {"value": F * 1e-9 / scipy_forward_rate(n, w, reps=2), "workers": w, "sample": f"scipy.fft.fftn complex128 {n}^3, best of 2 warm runs"}
         except Exception as exc:   # the extra legs never take the bench line down
             others["error"] = repr(exc)

@@ -41,6 +41,11 @@ __device__ __forceinline__ void tensor_g2s_2d(void* dst, const CUtensorMap* map,
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tensor_g2s_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tensor_s2g_2d(const CUtensorMap* map, int c0, int c1, const void* src)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
@@ -94,6 +99,36 @@ template <bool LINE> __device__ __forceinline__ void transform_tile(double2* buf
     cons_sync();
 }
 
+// X role: the tile arrives as C columns [pos][c] and leaves as C contiguous lines [c][pos]: the thread map changes from
+// column-major to line-major in the last exchange, whose buffer is XOR-swizzled so that both sides are conflict free
+__device__ __forceinline__ void transform_tile_x(double2* buf, const double2* lut, int tid)
+{
+    const int c_in = tid % C, t_in = tid / C, t_out = tid % TT, c_out = tid / TT;
+    double2 v[S::R];
+#pragma unroll
+    for (int u = 0; u < S::R; u++) v[u] = buf[(t_in + u * TT) * C + c_in];
+    stage_compute<S, 0, double, false>(v, t_in, lut, nullptr);
+    cons_sync();
+    exchange<false, 0>(v, buf, t_in, c_in);
+    stage_compute<S, 1, double, false>(v, t_in, lut, nullptr);
+    cons_sync();
+    {
+        constexpr int RAD = S::rad(1), NS = S::ns(1);
+        const int k = t_in % NS, j0 = (t_in - k) * RAD + k;
+#pragma unroll
+        for (int m = 0; m < RAD; m++) { const int pos = j0 + m * NS; buf[pos * C + (c_in ^ (pos & 7))] = v[m]; }
+        cons_sync();
+#pragma unroll
+        for (int u = 0; u < S::R; u++) { const int pos = t_out + u * TT; v[u] = buf[pos * C + (c_out ^ (pos & 7))]; }
+    }
+    stage_compute<S, 2, double, false>(v, t_out, lut, nullptr);
+    cons_sync();
+#pragma unroll
+    for (int u = 0; u < S::R; u++) buf[c_out * N + t_out + u * TT] = v[u];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    cons_sync();
+}
+
 struct Smem {
     unsigned char* base;
     __device__ __forceinline__ double2* slot(int i) const { return reinterpret_cast<double2*>(base + (size_t)i * TILE_BYTES); }
@@ -137,10 +172,14 @@ __global__ void __launch_bounds__(NCONS, 1) pass_tma(const double2* in, double2*
         const long long tile = tile_of(i);
         mbar_expect_tx(sm.full + s, TILE_BYTES);
         if (MODE == 0) bulk_g2s(sm.slot(s), in + tile * TILE_ELEMS, TILE_BYTES, sm.full + s);
-        else {
+        else if (MODE == 1) {
             const int a = (int)(tile / (N / C)), b = (int)(tile % (N / C));
             tensor_g2s_2d(sm.slot(s), &map_in, b * C * 2, a * N, sm.full + s);
             tensor_g2s_2d(sm.slot(s) + TILE_ELEMS / 2, &map_in, b * C * 2, a * N + N / 2, sm.full + s);
+        } else {   // X: tile (y = a, z group b): rows x = 0..N-1 of the 3-D tensor (z, y, x)
+            const int a = (int)(tile / (N / C)), b = (int)(tile % (N / C));
+            tensor_g2s_3d(sm.slot(s), &map_in, b * C * 2, a, 0, sm.full + s);
+            tensor_g2s_3d(sm.slot(s) + TILE_ELEMS / 2, &map_in, b * C * 2, a, N / 2, sm.full + s);
         }
     };
     if (tid == 0)
@@ -149,10 +188,11 @@ __global__ void __launch_bounds__(NCONS, 1) pass_tma(const double2* in, double2*
         const int s = (int)(i % NSLOT);
         mbar_wait(sm.full + s, (uint32_t)((i / NSLOT) & 1));
         if (MODE == 0) transform_tile<true>(sm.slot(s), sm.lut, tid);
-        else transform_tile<false>(sm.slot(s), sm.lut, tid);
+        else if (MODE == 1) transform_tile<false>(sm.slot(s), sm.lut, tid);
+        else transform_tile_x(sm.slot(s), sm.lut, tid);
         if (tid == 0) {
             const long long tile = tile_of(i);
-            if (MODE == 0) bulk_s2g(out + tile * TILE_ELEMS, sm.slot(s), TILE_BYTES);
+            if (MODE == 0 || MODE == 2) bulk_s2g(out + tile * TILE_ELEMS, sm.slot(s), TILE_BYTES);   // X: out[(y N + z) N + x], tile = y * 64 + z / 8
             else {
                 const int a = (int)(tile / (N / C)), b = (int)(tile % (N / C));
                 tensor_s2g_2d(&map_out, b * C * 2, a * N, sm.slot(s));
@@ -300,6 +340,41 @@ static CUtensorMap make_map(void* base, long long rows)
     return m;
 }
 
+static CUtensorMap make_map3(void* base, int nx)
+{
+    EncodeTiledFn fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&fn, cudaEnableDefault, &q));
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)N * 2, (cuuint64_t)N, (cuuint64_t)nx};           // z (doubles), y, x
+    cuuint64_t strides[2] = {(cuuint64_t)N * 16, (cuuint64_t)N * N * 16};
+    cuuint32_t box[3] = {(cuuint32_t)C * 2, 1, (cuuint32_t)N / 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled (3-D) failed: %d\n", (int)r); exit(1); }
+    return m;
+}
+
+// X: element (x, y, z) = wave along x with frequency f = (y + z) % N; output layout [y][z][x]
+__global__ void fill_x(double2* a)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)N * N * N) return;
+    const int z = (int)(i % N), y = (int)((i / N) % N), x = (int)(i / ((long long)N * N));
+    double sn, cs; sincospi(2.0 * (double)((long long)((y + z) % N) * x % N) / N, &sn, &cs);
+    a[i] = make_double2(cs, sn);
+}
+__global__ void check_x(const double2* a, double* maxerr)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)N * N * N) return;
+    const int x = (int)(i % N), z = (int)((i / N) % N), y = (int)(i / ((long long)N * N));
+    const double ex = x == (y + z) % N ? (double)N : 0.0;
+    const double err = fmax(fabs(a[i].x - ex), fabs(a[i].y));
+    if (err > 1e-9) atomicMax((unsigned long long*)maxerr, (unsigned long long)__double_as_longlong(err));
+}
+
 // plane wave per line / per plane; after the transform the energy sits in one bin
 __global__ void fill_lines(double2* a, long long nlines)
 {
@@ -382,6 +457,7 @@ int main(int argc, char** argv)
     CUtensorMap map_a = make_map(d_a, nlines), map_b = make_map(d_b, nlines);
     CK(cudaFuncSetAttribute(pass_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CK(cudaFuncSetAttribute(pass_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CK(cudaFuncSetAttribute(pass_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CK(cudaFuncSetAttribute(fused_t0_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const unsigned fb = (unsigned)((count + 255) / 256);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -410,6 +486,20 @@ int main(int argc, char** argv)
     for (int i = 0; i < iters; i++) pass_tma<1><<<sms, NCONS, SMEM_BYTES>>>(d_a, d_b, map_a, map_b, d_lut, ntiles);
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     printf("Y pass  TMA ring : %.3f ms  %.0f GB/s  err=%.2e\n", ms, bytes / ms * 1e-6, err); fflush(stdout);
+
+    // X pass (needs the full cube: 512 planes)
+    if (planes == N) {
+        CUtensorMap map3 = make_map3(d_a, planes);
+        fill_x<<<fb, 256>>>(d_a); CK(cudaMemset(d_err, 0, 8));
+        pass_tma<2><<<sms, NCONS, SMEM_BYTES>>>(d_a, d_b, map3, map_b, d_lut, ntiles);
+        CK(cudaGetLastError());
+        check_x<<<fb, 256>>>(d_b, d_err); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(&err, d_err, 8, cudaMemcpyDeviceToHost));
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; i++) pass_tma<2><<<sms, NCONS, SMEM_BYTES>>>(d_a, d_b, map3, map_b, d_lut, ntiles);
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+        printf("X pass  TMA ring : %.3f ms  %.0f GB/s  err=%.2e\n", ms, bytes / ms * 1e-6, err); fflush(stdout);
+    }
 
     // fused t0: a -> b (Z), b -> b (Y)
     unsigned long long* d_done; unsigned int* d_ticket;

@@ -342,12 +342,15 @@ class HeffteRef:
         return list(t), float(pair.value)
 
 
-def physical_core_cpus():
-    """One logical CPU per physical core among the CPUs this process may run on (hyperthread siblings dropped)."""
-    try:
-        allowed = sorted(os.sched_getaffinity(0))
-    except AttributeError:
-        allowed = list(range(os.cpu_count() or 1))
+def physical_core_cpus(allowed=None):
+    """One logical CPU per physical core among `allowed` (default: the CPUs the calling thread may run on -- pass the
+    process's set captured at start-up when an OpenMP runtime may have bound the main thread since); hyperthread
+    siblings are dropped."""
+    if allowed is None:
+        try:
+            allowed = sorted(os.sched_getaffinity(0))
+        except AttributeError:
+            allowed = list(range(os.cpu_count() or 1))
     seen, out = set(), []
     for c in allowed:
         try:
