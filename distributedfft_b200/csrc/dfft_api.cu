@@ -1637,7 +1637,8 @@ extern "C" int dfft_lines_destroy(dfft_lines_plan p)
 //   A: view the line as [n1][n2]; FFT along n1 (stride n2), multiply by W_n^(n2*k1), store transposed -> temp [n2][k1]
 //   B: FFT along n2 (stride n1) of temp, stored to the caller's buffer at [k2][k1] = natural order X[k1 + n1*k2]
 // -- what the reference does with its multi-upload axes and reorderFourStep = 1 (templateFFT.cpp:4007-4106, 5951).
-// EXPERIMENTAL until it has been run against the oracle on hardware: enabled with DFFT_EXPERIMENTAL_LONG=1.
+// Validated against numpy on B200 (tests/test_gpu_parity.py::test_four_step_long_lines, profiles/r2_pytest_gpu_1xB200.log);
+// DFFT_NO_LONG_LINES=1 restores the "unsupported length" answer.
 static int make_four_step(dfft_lines_plan p, int n, long long nlines, int precision, bool dry = false)
 {
     long long best1 = 0;
@@ -1696,8 +1697,8 @@ extern "C" int dfft_lines_plan_create(int n, long long stride, long long nlines,
     if (n < 1 || nlines < 0 || stride < 1 || (precision != DFFT_DOUBLE && precision != DFFT_FLOAT)) return fail(DFFT_EINVAL, "bad arguments");
     dfft_lines_plan p = new dfft_lines_plan_s;
     int rc = lines_plan_common(p, precision);
-    const char* lng = getenv("DFFT_EXPERIMENTAL_LONG");
-    if (!rc && !find_size_entry(n, precision) && stride == 1 && inner_dist == n && lng && atoi(lng) != 0) {
+    const char* nolong = getenv("DFFT_NO_LONG_LINES");
+    if (!rc && !find_size_entry(n, precision) && stride == 1 && inner_dist == n && !(nolong && atoi(nolong) != 0)) {
         rc = make_four_step(p, n, nlines, precision);
     } else {
         if (!rc) rc = make_line_pass(p->pass[0], n, stride, nlines, inner, inner_dist, outer_dist, precision);

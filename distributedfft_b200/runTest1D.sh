@@ -1,7 +1,7 @@
 #!/bin/bash
 # Batched 1-D sweep with the surface of the reference's templateFFT/batchTest/runTest1D_opt.sh (same lengths, same CSV
 # header, 2^26 points per run): geometric ladders of 2 (from 256), 3, 5 and 7 up to the reference's limits.
-# Lengths beyond one shared-memory line (6400 points in double) need DFFT_EXPERIMENTAL_LONG=1 (four-step plan);
+# Lengths beyond one shared-memory line (6400 points in double) run on the two-pass four-step plan;
 # what is still unsupported is reported and skipped.
 here="$(cd "$(dirname "$0")" && pwd)"
 iters=${NUM_ITER:-1000}

@@ -379,12 +379,10 @@ def test_compute_sanitizer_memcheck_and_racecheck():
         assert "ERROR SUMMARY: 0 errors" in r.stdout or "RACECHECK SUMMARY: 0 hazards" in r.stdout, (tool, r.stdout[-1500:])
 
 
-@pytest.mark.skipif(os.environ.get("DFFT_TEST_EXPERIMENTAL") != "1", reason="experimental four-step long lines: set DFFT_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("precision", [dfft.DOUBLE, dfft.FLOAT])
-def test_four_step_long_lines(precision, monkeypatch):
-    """Lines longer than one shared-memory line go through the two-pass four-step plan (DFFT_EXPERIMENTAL_LONG=1):
-    the lengths the reference's Test_1D sweep reaches with multi-upload axes (runTest1D_opt.sh:5-21)."""
-    monkeypatch.setenv("DFFT_EXPERIMENTAL_LONG", "1")
+def test_four_step_long_lines(precision):
+    """Lines longer than one shared-memory line go through the two-pass four-step plan: the lengths the reference's
+    Test_1D sweep reaches with multi-upload axes (templateFFT.cpp:4007-4106, runTest1D_opt.sh:5-21)."""
     tol = 1e-12 if precision == dfft.DOUBLE else 5e-6
     rng = np.random.default_rng(23)
     for n in (8192, 16384, 131072, 6561, 19683, 78125, 16807, 12000):
