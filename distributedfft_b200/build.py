@@ -22,8 +22,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 
-LIB_SOURCES = ["dfft_api.cu", "dfft_kernels_common.cu", "dfft_kernels_generic.cu", "dfft_kernels_f64.cu", "dfft_kernels_f32.cu"]
-HEADERS = ["fft_core.cuh", "fft_passes.cuh", "fft_generic.cuh", "dfft_kernels.cuh", "dfft_kernels_inst.cuh", os.path.join("..", "..", "include", "dfft.h")]
+LIB_SOURCES = ["dfft_api.cu", "dfft_kernels_common.cu", "dfft_kernels_generic.cu", "dfft_kernels_f64.cu", "dfft_kernels_f32.cu", "dfft_kernels_tma.cu"]
+HEADERS = ["fft_core.cuh", "fft_passes.cuh", "fft_generic.cuh", "fft_tma.cuh", "dfft_kernels.cuh", "dfft_kernels_inst.cuh", os.path.join("..", "..", "include", "dfft.h")]
 
 
 def _newer(target, deps):

@@ -22,6 +22,7 @@
 
 #include "../../include/dfft.h"
 #include "dfft_kernels.cuh"
+#include "fft_tma.cuh"
 
 using namespace dfft;
 
@@ -396,6 +397,10 @@ struct dfft_plan_s {
     const SizeEntry *ez = nullptr, *ey = nullptr, *ex = nullptr;   // axes N2 (Z), N1 (Y), N0 (X)
     void *lut_z = nullptr, *lut_y = nullptr, *lut_x = nullptr;
     void* lut_xn = nullptr;   // X axis with the strided-local schedule (DFFT_NATURAL_SPECTRUM)
+    // TMA-pipelined pass kernels (fft_tma.cuh) for the axes that have an instantiation: used for the passes whose load and
+    // store are both local and un-chunked (Z, natural Y, X with the fused transpose); nullptr -> register-staged kernels
+    const TmaEntry *tz = nullptr, *ty = nullptr, *tx = nullptr;
+    void *lut_tz = nullptr, *lut_ty = nullptr, *lut_tx = nullptr;
     bool natural = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -586,6 +591,18 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
         CUP(upload_lut<float>(&p->lut_x, ex->x_nstages, ex->x_rad));
     }
     if (!dry) CUP(cudaGetLastError());
+    if (!dry && !(flags & DFFT_NO_TMA)) {
+        p->tz = find_tma_entry((int)n2, precision);
+        p->ty = find_tma_entry((int)n1, precision);
+        p->tx = find_tma_entry((int)n0, precision);
+        const TmaEntry* te[3] = {p->tz, p->ty, p->tx};
+        void** tl[3] = {&p->lut_tz, &p->lut_ty, &p->lut_tx};
+        for (int i = 0; i < 3; i++) {
+            if (!te[i]) continue;
+            if (precision == DFFT_DOUBLE) CUP(upload_lut<double>(tl[i], te[i]->nstages, te[i]->rad));
+            else CUP(upload_lut<float>(tl[i], te[i]->nstages, te[i]->rad));
+        }
+    }
     if (flags & DFFT_NATURAL_SPECTRUM) {
         // spectrum kept in natural [x][y][z] order: one device only (with P > 1 it would need a second all-to-all)
         if (P != 1) return bail(fail(DFFT_EUNSUPPORTED, "DFFT_NATURAL_SPECTRUM needs a single device (a distributed natural-order spectrum would take a second exchange)"));
@@ -794,6 +811,9 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->lut_y) cudaFree(p->lut_y);
     if (p->lut_x) cudaFree(p->lut_x);
     if (p->lut_xn) cudaFree(p->lut_xn);
+    if (p->lut_tz) cudaFree(p->lut_tz);
+    if (p->lut_ty) cudaFree(p->lut_ty);
+    if (p->lut_tx) cudaFree(p->lut_tx);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& pe : p->pev) for (auto& e : pe) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -837,10 +857,43 @@ template <typename T> struct Pass {
         p->launches++;
         return 0;
     }
+    // one TMA-pipelined pass (fft_tma.cuh).  Tensor sides are described as (base, d1, d2, s1, s2, axis): a 3-D tensor of
+    // complex elements, row length `d0`, dim1/dim2 extents and element strides, transform axis = tensor dim `axis` (1 or 2)
+    struct TmaTensor { void* base; long long d0, d1, d2, s1, s2; };
+    static int launch_tma(dfft_plan p, const TmaEntry* e, int mode, TmaArgs<T>& a, const TmaTensor* tin, const TmaTensor* tout, int axis,
+                          cudaStream_t st = nullptr)
+    {
+        if (!st) st = p->stream;
+        alignas(64) unsigned char mi[128], mo[128];
+        const int rows = e->rows;
+        const TmaTensor* ts[2] = {tin, tout};
+        unsigned char* ms[2] = {mi, mo};
+        for (int k = 0; k < 2; k++) {
+            if (!ts[k]) continue;
+            const int b1 = mode == TMA_Y ? rows : 1, b2 = mode == TMA_Y ? 1 : rows;
+            const int rc = tma_encode_3d(ms[k], ts[k]->base, p->prec, ts[k]->d0, ts[k]->d1, ts[k]->d2, ts[k]->s1, ts[k]->s2, e->C, b1, b2);
+            if (rc != 0) return fail(DFFT_ECUDA, "cuTensorMapEncodeTiled failed (%d) for a %lldx%lldx%lld tensor", rc, ts[k]->d0, ts[k]->d1, ts[k]->d2);
+        }
+        a.inv = p->direction == DFFT_BACKWARD ? 1 : 0;
+        if (!p->in_pipe) ev_record(p, p->pev[axis][0]);
+        cudaError_t err = e->launch(mode, &a, tin ? mi : nullptr, tout ? mo : nullptr, p->sms, st);
+        if (!p->in_pipe) ev_record(p, p->pev[axis][1]);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "TMA pass launch (mode %d, N=%d) failed: %s", mode, e->N, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
+    }
     // contiguous lines of length N2 (n0l*N1 lines), src -> dst (in place when equal)
     static int z_pass(dfft_plan p, const void* src, void* dst, bool scale)
     {
         const Geom& g = p->g;
+        if (p->tz && !p->dry && (p->n0l * g.n1) % p->tz->C == 0) {
+            TmaArgs<T> t{};
+            t.in = (const cx<T>*)src; t.out = (cx<T>*)dst; t.lut = (const cx<T>*)p->lut_tz;
+            t.ntiles = p->n0l * g.n1 / p->tz->C; t.G = (int)std::min<long long>(t.ntiles, 0x7fffffff);
+            t.in_SA = t.out_SA = (long long)t.G * p->tz->C * g.n2;   // a = tile / G: only needed beyond 2^31 tiles
+            t.do_scale = scale ? 1 : 0; t.scale = (T)(1.0 / ((double)g.n0 * (double)g.n1 * (double)g.n2));
+            return launch_tma(p, p->tz, TMA_Z, t, nullptr, nullptr, 0);
+        }
         TileArgs<T> a{};
         const int C = p->ez->z_C;
         const long long nlines = p->n0l * g.n1;
@@ -855,6 +908,13 @@ template <typename T> struct Pass {
     static int y_pass(dfft_plan p, const void* src, void* dst, int mode, void* const* chunk_base)
     {
         const Geom& g = p->g;
+        if (mode == 0 && p->ty && !p->dry && g.n2 % p->ty->C == 0) {
+            TmaArgs<T> t{};
+            t.lut = (const cx<T>*)p->lut_ty;
+            t.G = (int)(g.n2 / p->ty->C); t.ntiles = p->n0l * t.G;
+            TmaTensor ti{(void*)src, g.n2, g.n1, p->n0l, g.n2, g.n1 * g.n2}, to{dst, g.n2, g.n1, p->n0l, g.n2, g.n1 * g.n2};
+            return launch_tma(p, p->ty, TMA_Y, t, &ti, &to, 1);
+        }
         TileArgs<T> a{};
         const int C = mode == 1 ? p->ey->p_C : p->ey->s_C;
         a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_y;
@@ -976,6 +1036,13 @@ template <typename T> struct Pass {
     static int x_fwd(dfft_plan p, const void* src, void* dst)
     {
         const Geom& g = p->g;
+        if (p->tx && !p->dry && g.n2 % p->tx->C == 0) {
+            TmaArgs<T> t{};
+            t.lut = (const cx<T>*)p->lut_tx; t.out = (cx<T>*)dst;
+            t.G = (int)(g.n2 / p->tx->C); t.ntiles = p->n1l * t.G; t.out_SA = g.n2 * g.n0;
+            TmaTensor ti{(void*)src, g.n2, p->n1l, g.n0, g.n2, p->n1l * g.n2};
+            return launch_tma(p, p->tx, TMA_XF, t, &ti, nullptr, 2);
+        }
         TileArgs<T> a{};
         const int C = p->ex->x_C;
         a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_x;
@@ -1042,6 +1109,14 @@ template <typename T> struct Pass {
     static int x_part(dfft_plan p, const void* rpart, void* dst, long long zk, int k, int cap, cudaStream_t st)
     {
         const Geom& g = p->g;
+        // the TMA kernel takes the whole SM (one CTA, 3-slot ring): only for a part that overlaps nothing (the last one)
+        if (cap == 0 && p->tx && !p->dry && zk % p->tx->C == 0) {
+            TmaArgs<T> t{};
+            t.lut = (const cx<T>*)p->lut_tx; t.out = (cx<T>*)dst + k * zk * g.n0;
+            t.G = (int)(zk / p->tx->C); t.ntiles = p->n1l * t.G; t.out_SA = g.n2 * g.n0;
+            TmaTensor ti{(void*)rpart, zk, p->n1l, g.n0, zk, p->n1l * zk};
+            return launch_tma(p, p->tx, TMA_XF, t, &ti, nullptr, 2, st);
+        }
         TileArgs<T> a{};
         const int C = p->ex->x_C;
         a.in = (const cx<T>*)rpart; a.out = (cx<T>*)dst + k * zk * g.n0; a.lut = (const cx<T>*)p->lut_x;
@@ -1055,6 +1130,13 @@ template <typename T> struct Pass {
     static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base)
     {
         const Geom& g = p->g;
+        if (!chunk_base && p->tx && !p->dry && g.n2 % p->tx->C == 0) {
+            TmaArgs<T> t{};
+            t.lut = (const cx<T>*)p->lut_tx; t.in = (const cx<T>*)src;
+            t.G = (int)(g.n2 / p->tx->C); t.ntiles = p->n1l * t.G; t.in_SA = g.n2 * g.n0;
+            TmaTensor to{dst, g.n2, p->n1l, g.n0, g.n2, p->n1l * g.n2};
+            return launch_tma(p, p->tx, TMA_XB, t, nullptr, &to, 2);
+        }
         TileArgs<T> a{};
         const int C = p->ex->x_C;
         a.in = (const cx<T>*)src; a.out = (cx<T>*)dst; a.lut = (const cx<T>*)p->lut_x;

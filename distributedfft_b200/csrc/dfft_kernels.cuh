@@ -50,6 +50,18 @@ struct SizeEntry {
     const void* gen;      // run-time schedule (GenSched) of a generic-length entry, nullptr for tuned lengths
 };
 
+// TMA-pipelined pass kernels (fft_tma.cuh), instantiated for the lengths whose C-line tile fills a 64 KB ring slot
+typedef cudaError_t (*TmaLaunchFn)(int mode, const void* tma_args, const void* map_in, const void* map_out, int sm_count, cudaStream_t stream);
+struct TmaEntry {
+    int N, prec;
+    int C;                 // lines / columns per tile
+    int rows;              // rows per tensor copy (transform length split into N / rows boxes)
+    int nstages, rad[24];  // radix schedule (its twiddle table: build_lut)
+    TmaLaunchFn launch;
+};
+const TmaEntry* find_tma_entry(int N, int prec);   // nullptr: no instantiation, driver too old, or DFFT_TMA=0
+int tma_encode_3d(void* map, void* base, int prec, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1, int b2);
+
 // tuned entry if the length is in the table, else a generic (run-time scheduled) entry for 2..13-smooth lengths,
 // else nullptr.  DFFT_GENERIC=1 forces the generic kernel (tests).
 const SizeEntry* find_size_entry(int N, int prec);

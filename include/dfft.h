@@ -66,6 +66,11 @@ extern "C" {
                                     overlap t0 -- the reference has no overlap at all (fft_mpi_3d_api.cpp:610-672).
                                     env DFFT_PIPELINE=0 also disables it, DFFT_PARTS=k picks the number of parts */
 
+#define DFFT_NO_TMA 512u          /* use the register-staged pass kernels everywhere.  Default: passes whose load and store are both
+                                    local and un-chunked (Z, natural Y, X) run on the TMA-pipelined kernels (fft_tma.cuh: 3-slot
+                                    shared-memory ring fed and drained by cp.async.bulk / cp.async.bulk.tensor) for the lengths
+                                    that have an instantiation; env DFFT_TMA=0 has the same effect */
+
 #define DFFT_EINVAL (-1)
 #define DFFT_ECUDA (-2)
 #define DFFT_EUNSUPPORTED (-3)

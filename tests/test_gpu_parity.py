@@ -217,13 +217,38 @@ def test_fused_t0_is_bitwise_the_two_sweep_t0(n, n0):
     for direction in (FORWARD, BACKWARD):
         inp = A.reshape(-1) if direction == FORWARD else A.transpose(1, 2, 0).reshape(-1)
         a = run_slab(n0, n, n, 1, direction, [inp], repeat=3, refill=False, flags=dfft.FORCE_FUSE)
-        b = run_slab(n0, n, n, 1, direction, [inp], repeat=3, refill=False, flags=dfft.NO_FUSE)
+        b = run_slab(n0, n, n, 1, direction, [inp], repeat=3, refill=False, flags=dfft.NO_FUSE | dfft.NO_TMA)   # same kernels as the fused roles
         assert a[0]["fused"] and not b[0]["fused"]
         assert a[0]["launches"] == 2 and b[0]["launches"] == 3
         assert np.array_equal(a[0]["buf2"], b[0]["buf2"]), (n, n0, direction)
     ref = np.fft.fftn(A).transpose(1, 2, 0).reshape(-1)
     f = run_slab(n0, n, n, 1, FORWARD, [A.reshape(-1)], flags=dfft.FORCE_FUSE)
     assert np.abs(f[0]["buf2"] - ref).max() <= 1e-12 * np.log2(A.size) * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n0,n1,n2,precision", [(512, 512, 16, dfft.DOUBLE), (16, 512, 512, dfft.DOUBLE), (24, 1024, 1024, dfft.DOUBLE), (256, 256, 256, dfft.DOUBLE),
+                                                 (8, 768, 768, dfft.DOUBLE), (512, 32, 512, dfft.FLOAT), (16, 1024, 1024, dfft.FLOAT), (768, 768, 16, dfft.FLOAT)])
+def test_tma_pipelined_passes_match_the_register_staged_kernels(n0, n1, n2, precision):
+    """The TMA-ring pass kernels (fft_tma.cuh: Z, natural Y, X with the fused transpose, forward and backward) against the
+    register-staged fft_tile_kernel on the same data -- bit for bit where both use the same radix schedule (512: 8.8.8),
+    to rounding otherwise -- and against numpy.  Shapes mix axes with and without a TMA instantiation."""
+    rng = np.random.default_rng(n0 + n1 + n2)
+    npdt = CDT[precision][0]
+    A = (rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))).astype(npdt)
+    ref = np.fft.fftn(A.astype(np.complex128)).transpose(1, 2, 0).reshape(-1)
+    tol = 1e-12 * np.log2(A.size) if precision == dfft.DOUBLE else 5e-6
+    a = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)], precision=precision, repeat=2, refill=False)
+    b = run_slab(n0, n1, n2, 1, FORWARD, [A.reshape(-1)], precision=precision, flags=dfft.NO_TMA)
+    assert np.abs(a[0]["buf2"] - ref).max() <= tol * np.abs(ref).max()
+    assert np.abs(a[0]["buf2"] - b[0]["buf2"]).max() <= tol * np.abs(ref).max()
+    if precision == dfft.DOUBLE and {n0, n1, n2} <= {512, 16}:
+        assert np.array_equal(a[0]["buf2"], b[0]["buf2"])
+    spec = a[0]["buf2"]
+    ba = run_slab(n0, n1, n2, 1, BACKWARD, [spec], precision=precision, flags=dfft.SCALE_BACKWARD)
+    bb = run_slab(n0, n1, n2, 1, BACKWARD, [spec], precision=precision, flags=dfft.SCALE_BACKWARD | dfft.NO_TMA)
+    rt = 1e-11 if precision == dfft.DOUBLE else 5e-4
+    assert np.abs(ba[0]["buf2"] - A.reshape(-1)).max() <= rt
+    assert np.abs(ba[0]["buf2"] - bb[0]["buf2"]).max() <= rt
 
 
 def test_host_buffer_entry_points_two_plans_in_flight():
