@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../fft_core.cuh"
+#include "../fft_tma.cuh"
 
 using namespace dfft;
 
@@ -413,6 +414,14 @@ __global__ void check_cols(const double2* a, int planes, double* maxerr)
     const double err = fmax(fabs(a[i].x - ex), fabs(a[i].y));
     if (err > 1e-9) atomicMax((unsigned long long*)maxerr, (unsigned long long)__double_as_longlong(err));
 }
+__global__ void fill_random(double2* a, long long n)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long s = 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
+    a[i] = make_double2((double)(s & 0xffffff) * (1.0 / 16777216.0), (double)((s >> 24) & 0xffffff) * (1.0 / 16777216.0));
+}
 // 2-D: plane p holds e^{2 pi i (fy y + fz z)/N}, fy = 7p % N, fz = 13p % N  ->  N^2 at (fy, fz)
 __global__ void fill_2d(double2* a, int planes)
 {
@@ -500,6 +509,75 @@ int main(int argc, char** argv)
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
         printf("X pass  TMA ring : %.3f ms  %.0f GB/s  err=%.2e\n", ms, bytes / ms * 1e-6, err); fflush(stdout);
     }
+
+    // the LIBRARY kernels (fft_tma.cuh) in the same harness, plane-wave and random data, short and long timing loops
+    {
+        using LS = Sched<512, 8, 8, 8, 8>;
+        CK(cudaFuncSetAttribute(fft_tma_pass_kernel<LS, double, 8, TMA_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGeom<LS, double, 8>::SMEM));
+        CK(cudaFuncSetAttribute(fft_tma_pass_kernel<LS, double, 8, TMA_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGeom<LS, double, 8>::SMEM));
+        CK(cudaFuncSetAttribute(fft_tma_pass_kernel<LS, double, 8, TMA_XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGeom<LS, double, 8>::SMEM));
+        const size_t lsm = TmaGeom<LS, double, 8>::SMEM;
+        EncodeTiledFn fn = nullptr; cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&fn, cudaEnableDefault, &q));
+        auto enc3 = [&](void* base, int b1, int b2) {
+            CUtensorMap m;
+            cuuint64_t dims[3] = {(cuuint64_t)N * 2, (cuuint64_t)N, (cuuint64_t)planes};
+            cuuint64_t strides[2] = {(cuuint64_t)N * 16, (cuuint64_t)N * N * 16};
+            cuuint32_t box[3] = {16, (cuuint32_t)b1, (cuuint32_t)b2};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
+            return m;
+        };
+        CUtensorMap dummy{};
+        for (int rnd = 0; rnd < 2; rnd++) {
+            if (rnd) { fill_random<<<fb, 256>>>(d_a, count); fill_random<<<fb, 256>>>(d_b, count); }
+            else fill_lines<<<fb, 256>>>(d_a, nlines);
+            CK(cudaDeviceSynchronize());
+            for (int reps : {5, 40}) {
+                for (int inplace = 0; inplace < 2; inplace++) {
+                    double2* o = inplace ? d_a : d_b;
+                    TmaArgs<double> A{}; A.lut = d_lut; A.scale = 1.0;
+                    // Z
+                    A.in = d_a; A.out = o; A.ntiles = ntiles; A.G = (int)ntiles; A.in_SA = A.out_SA = 0;
+                    cudaEventRecord(e0);
+                    for (int i = 0; i < reps; i++) fft_tma_pass_kernel<LS, double, 8, TMA_Z><<<sms, 512, lsm>>>(A, dummy, dummy);
+                    cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError()); cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+                    printf("LIB Z   %s data, %2d reps, %s: %.3f ms  %.0f GB/s\n", rnd ? "random" : "wave  ", reps, inplace ? "in place    " : "out of place", ms, bytes / ms * 1e-6);
+                    // Y
+                    CUtensorMap mi = enc3(d_a, 256, 1), mo = enc3(o, 256, 1);
+                    A.G = N / 8; A.ntiles = (long long)planes * A.G;
+                    cudaEventRecord(e0);
+                    for (int i = 0; i < reps; i++) fft_tma_pass_kernel<LS, double, 8, TMA_Y><<<sms, 512, lsm>>>(A, mi, mo);
+                    cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError()); cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+                    printf("LIB Y   %s data, %2d reps, %s: %.3f ms  %.0f GB/s\n", rnd ? "random" : "wave  ", reps, inplace ? "in place    " : "out of place", ms, bytes / ms * 1e-6);
+                    // X (out of place only)
+                    if (!inplace && planes == N) {
+                        CUtensorMap mx = enc3(d_a, 1, 256);
+                        A.out = d_b; A.out_SA = (long long)N * N;
+                        cudaEventRecord(e0);
+                        for (int i = 0; i < reps; i++) fft_tma_pass_kernel<LS, double, 8, TMA_XF><<<sms, 512, lsm>>>(A, mx, dummy);
+                        cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError()); cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+                        printf("LIB XF  %s data, %2d reps, out of place: %.3f ms  %.0f GB/s\n", rnd ? "random" : "wave  ", reps, ms, bytes / ms * 1e-6);
+                    }
+                    fflush(stdout);
+                }
+            }
+        }
+        // the prototype's own kernels on random data, long loop
+        for (int reps : {5, 40}) {
+            cudaEventRecord(e0);
+            for (int i = 0; i < reps; i++) pass_tma<0><<<sms, NCONS, SMEM_BYTES>>>(d_a, d_b, map_a, map_b, d_lut, ntiles);
+            cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+            printf("PROTO Z random data, %2d reps: %.3f ms  %.0f GB/s\n", reps, ms, bytes / ms * 1e-6);
+            cudaEventRecord(e0);
+            for (int i = 0; i < reps; i++) pass_tma<1><<<sms, NCONS, SMEM_BYTES>>>(d_a, d_b, map_a, map_b, d_lut, ntiles);
+            cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+            printf("PROTO Y random data, %2d reps: %.3f ms  %.0f GB/s\n", reps, ms, bytes / ms * 1e-6);
+        }
+    }
+    if (getenv("TMA_T0_SKIP_FUSED")) return 0;
 
     // fused t0: a -> b (Z), b -> b (Y)
     unsigned long long* d_done; unsigned int* d_ticket;
