@@ -886,7 +886,7 @@ template <typename T> struct Pass {
     static int z_pass(dfft_plan p, const void* src, void* dst, bool scale)
     {
         const Geom& g = p->g;
-        if (p->tz && !p->dry && (p->n0l * g.n1) % p->tz->C == 0) {
+        if (p->tz && (p->tz->use & (1u << TMA_Z)) && !p->dry && (p->n0l * g.n1) % p->tz->C == 0) {
             TmaArgs<T> t{};
             t.in = (const cx<T>*)src; t.out = (cx<T>*)dst; t.lut = (const cx<T>*)p->lut_tz;
             t.ntiles = p->n0l * g.n1 / p->tz->C; t.G = (int)std::min<long long>(t.ntiles, 0x7fffffff);
@@ -908,7 +908,7 @@ template <typename T> struct Pass {
     static int y_pass(dfft_plan p, const void* src, void* dst, int mode, void* const* chunk_base)
     {
         const Geom& g = p->g;
-        if (mode == 0 && p->ty && !p->dry && g.n2 % p->ty->C == 0) {
+        if (mode == 0 && p->ty && (p->ty->use & (1u << TMA_Y)) && !p->dry && g.n2 % p->ty->C == 0) {
             TmaArgs<T> t{};
             t.lut = (const cx<T>*)p->lut_ty;
             t.G = (int)(g.n2 / p->ty->C); t.ntiles = p->n0l * t.G;
@@ -1036,7 +1036,7 @@ template <typename T> struct Pass {
     static int x_fwd(dfft_plan p, const void* src, void* dst)
     {
         const Geom& g = p->g;
-        if (p->tx && !p->dry && g.n2 % p->tx->C == 0) {
+        if (p->tx && (p->tx->use & (1u << TMA_XF)) && !p->dry && g.n2 % p->tx->C == 0) {
             TmaArgs<T> t{};
             t.lut = (const cx<T>*)p->lut_tx; t.out = (cx<T>*)dst;
             t.G = (int)(g.n2 / p->tx->C); t.ntiles = p->n1l * t.G; t.out_SA = g.n2 * g.n0;
@@ -1110,7 +1110,7 @@ template <typename T> struct Pass {
     {
         const Geom& g = p->g;
         // the TMA kernel takes the whole SM (one CTA, 3-slot ring): only for a part that overlaps nothing (the last one)
-        if (cap == 0 && p->tx && !p->dry && zk % p->tx->C == 0) {
+        if (cap == 0 && p->tx && (p->tx->use & (1u << TMA_XF)) && !p->dry && zk % p->tx->C == 0) {
             TmaArgs<T> t{};
             t.lut = (const cx<T>*)p->lut_tx; t.out = (cx<T>*)dst + k * zk * g.n0;
             t.G = (int)(zk / p->tx->C); t.ntiles = p->n1l * t.G; t.out_SA = g.n2 * g.n0;
@@ -1130,7 +1130,7 @@ template <typename T> struct Pass {
     static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base)
     {
         const Geom& g = p->g;
-        if (!chunk_base && p->tx && !p->dry && g.n2 % p->tx->C == 0) {
+        if (!chunk_base && p->tx && (p->tx->use & (1u << TMA_XB)) && !p->dry && g.n2 % p->tx->C == 0) {
             TmaArgs<T> t{};
             t.lut = (const cx<T>*)p->lut_tx; t.in = (const cx<T>*)src;
             t.G = (int)(g.n2 / p->tx->C); t.ntiles = p->n1l * t.G; t.in_SA = g.n2 * g.n0;

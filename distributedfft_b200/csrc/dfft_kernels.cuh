@@ -58,6 +58,8 @@ struct TmaEntry {
     int rows;              // rows per tensor copy (transform length split into N / rows boxes)
     int nstages, rad[24];  // radix schedule (its twiddle table: build_lut)
     TmaLaunchFn launch;
+    unsigned use;          // bit m set: mode m (TMA_Z, TMA_Y, TMA_XF, TMA_XB) beats the register-staged kernel on B200
+                           // (profiles/r2_sweep_tma_vs_register_1gpu.log); DFFT_TMA=2 uses every mode, DFFT_TMA=0 none
 };
 const TmaEntry* find_tma_entry(int N, int prec);   // nullptr: no instantiation, driver too old, or DFFT_TMA=0
 int tma_encode_3d(void* map, void* base, int prec, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1, int b2);
