@@ -66,7 +66,9 @@ def build(force: bool = False, tools: bool = False, verbose: bool = False, exper
                 if verbose and out.strip():
                     print(out)
     if force or jobs or _newer(LIB, objs):
-        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"])
+        # link to a temporary name and rename: a snapshot taken while we build never sees a half-written library
+        _run([NVCC] + ARCH + ["-shared", "-o", LIB + ".tmp"] + objs + ["-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"])
+        os.replace(LIB + ".tmp", LIB)
     drv = os.path.join(HERE, "driver", "distFFT.cpp")
     if os.path.exists(drv) and (force or _newer(DRIVER, [drv, LIB, os.path.join(HERE, "..", "include", "fft_mpi_3d_api.h")])):
         _run([NVCC] + ARCH + ["-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", "-I", os.path.join(HERE, "..", "include"), drv, "-o", DRIVER,

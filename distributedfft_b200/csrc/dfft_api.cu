@@ -447,6 +447,7 @@ struct dfft_plan_s {
 // symbolic device address of a describe-only plan: device d (0-based), buffer id b: 1 bufferDev1, 2 bufferDev2 / user out,
 // 3 work / receive buffer, 4 intermediate of the single-kernel path, 5 user in
 static inline void* fake_addr(int d, int b) { return (void*)((((unsigned long long)(d + 1)) << 44) | (((unsigned long long)b) << 40)); }
+static inline char* eoff(void* base, long long elems, size_t esz) { return (char*)base + (size_t)elems * esz; }
 static inline cudaError_t ev_record(dfft_plan p, cudaEvent_t e) { return p->dry ? cudaSuccess : cudaEventRecord(e, p->stream); }
 static inline cudaError_t ev_record_on(dfft_plan p, cudaEvent_t e, cudaStream_t st) { return p->dry ? cudaSuccess : cudaEventRecord(e, st); }
 static inline cudaError_t stream_wait(dfft_plan p, cudaStream_t st, cudaEvent_t e) { return p->dry ? cudaSuccess : cudaStreamWaitEvent(st, e, 0); }
@@ -701,12 +702,13 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
     {
         // stream-pipelined forward (z-parts): send side and receive side on two streams, see fwd_pipelined
         const char* env = getenv("DFFT_PIPELINE");
-        bool want = P > 1 && direction == DFFT_FORWARD && !p->overlap && (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_NCCL);
+        bool want = P > 1 && !p->overlap && (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_NCCL);
+        if (direction == DFFT_BACKWARD && getenv("DFFT_PIPELINE_BWD") && !strcmp(getenv("DFFT_PIPELINE_BWD"), "0")) want = false;
         if (env) want = want && strcmp(env, "0") != 0;
         if (flags & DFFT_NO_PIPELINE) want = false;
         if (xmode == DFFT_EXCHANGE_NCCL && (n0 % P || n1 % P)) want = false;   // ncclAlltoAll parts need equal chunks
         if (want) {
-            const int cy = ey->p_C, cx_ = ex->x_C;
+            const int cy = direction == DFFT_FORWARD ? ey->p_C : ey->s_C, cx_ = ex->x_C;
             const int m = cy > cx_ ? cy : cx_;
             int K = 0;
             if (m % cy == 0 && m % cx_ == 0) {
@@ -722,7 +724,7 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
                 p->pipe = true;
                 if (dry) { p->mid = fake_addr(dev_idx, 4); p->sendbuf = fake_addr(dev_idx, 6); }
                 else {
-                    if (!p->mid) CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
+                    if (!p->mid && direction == DFFT_FORWARD) CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
                     if (xmode == DFFT_EXCHANGE_NCCL) {
                         CUP(cudaMalloc(&p->sendbuf, (size_t)p->max_count * p->esz));
                         CUP(cudaStreamCreateWithFlags(&p->stream3, cudaStreamNonBlocking));
@@ -1126,6 +1128,75 @@ template <typename T> struct Pass {
         a.max_ctas_per_sm = cap;
         return launch(p, p->ex, PK_XF, a, -1, st);
     }
+    // ---- z-part variants of the BACKWARD passes (stream-pipelined backward) --------------------------------------------------
+    // inverse X pass of one z-part: src[y_l][z in part][x] -> chunk p (= the x-planes of destination device p) at chunk_base[p],
+    // laid out [x_l][y_l][z'] with row length zk
+    static int xb_part(dfft_plan p, const void* src, long long zk, int k, void* const* chunk_base, int cap)
+    {
+        const Geom& g = p->g;
+        TileArgs<T> a{};
+        const int C = p->ex->x_C;
+        a.in = (const cx<T>*)src + k * zk * g.n0; a.out = nullptr; a.lut = (const cx<T>*)p->lut_x;
+        a.G = (int)cdiv(zk, C); a.W = (int)zk; a.ntiles = p->n1l * a.G;
+        a.ia = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
+        a.oa = Affine{0, C, 1, p->n1l * zk};
+        a.co.ediv = (int)g.xd(); a.co.nchunks = p->P;
+        for (int q = 0; q < p->P; q++) { a.co.cptr[q] = chunk_base[q]; a.co.SAq[q] = zk; }
+        if (p->xmode == DFFT_EXCHANGE_P2P && !p->dry && p->done_ctr) {
+            a.sig_n = p->P; a.sig_val = p->epoch; a.done_ctr = p->done_ctr + k;
+            for (int q = 0; q < p->P; q++) a.sig[q] = &p->peer_sync[q]->part_arrive[k][p->me];
+        }
+        a.max_ctas_per_sm = cap;
+        return launch(p, p->ex, PK_XB_CO, a);
+    }
+    // inverse Y pass of one z-part on the receive side: rpart = [sender q][x_l][y_l(q)][z'] -> dst[x_l][y][z in part]
+    static void yinv_part_args(dfft_plan p, TileArgs<T>& a, const void* rpart, void* dst, long long zk, int k, int C)
+    {
+        const Geom& g = p->g;
+        a.in = nullptr; a.out = (cx<T>*)dst + k * zk; a.lut = (const cx<T>*)p->lut_y;
+        a.G = (int)cdiv(zk, C); a.W = (int)zk; a.ntiles = p->n0l * a.G;
+        a.ia = Affine{0, C, 1, zk};
+        a.oa = Affine{g.n1 * g.n2, C, 1, g.n2};
+        a.ci.ediv = (int)g.yd(); a.ci.nchunks = p->P;
+        for (int q = 0; q < p->P; q++) { a.ci.cptr[q] = eoff((void*)rpart, (long long)q * p->n0l * g.yd() * zk, p->esz); a.ci.SAq[q] = g.n1l(q) * zk; }
+    }
+    static int yinv_part(dfft_plan p, const void* rpart, void* dst, long long zk, int k, int cap, cudaStream_t st)
+    {
+        TileArgs<T> a{};
+        yinv_part_args(p, a, rpart, dst, zk, k, p->ey->s_C);
+        a.max_ctas_per_sm = cap;
+        return launch(p, p->ey, PK_Y_CI, a, -1, st);
+    }
+    // the LAST part's inverse Y pass completes every plane: it runs fused with the inverse Z pass (fft_fused2_kernel, Y then Z)
+    static int yz_fused_last_part(dfft_plan p, const void* rpart, void* dst, long long zk, int k, bool scale, cudaStream_t st)
+    {
+        const Geom& g = p->g;
+        const SizeEntry* e = p->ez;
+        TileArgs<T> z{}, y{};
+        const int CZ = e->f_zC, CY = e->s_C;
+        yinv_part_args(p, y, rpart, dst, zk, k, CY);
+        y.inv = 1;
+        z.lut = (const cx<T>*)p->lut_z; z.inv = 1;
+        z.G = (int)cdiv(g.n1, CZ); z.W = (int)g.n1; z.ntiles = p->n0l * z.G;
+        z.ia = Affine{g.n1 * g.n2, (long long)CZ * g.n2, g.n2, 1}; z.oa = z.ia;
+        z.in = (const cx<T>*)dst; z.out = (cx<T>*)dst;
+        z.do_scale = scale ? 1 : 0; z.scale = (T)(1.0 / ((double)g.n0 * (double)g.n1 * (double)g.n2));
+        FusedCtl c{};
+        c.plane_done = p->plane_done; c.ticket = p->ticket; c.planes = p->n0l;
+        c.GA = y.G; c.GB = z.G;
+        c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
+        c.lag = p->lag;
+        if (p->dry) {
+            record_op<T>(p, "fusedY", 1, e->N, CY, true, false, false, y);
+            record_op<T>(p, "fusedZ", 1, e->N, CZ, false, false, false, z);
+            p->launches++;
+            return 0;
+        }
+        cudaError_t err = e->fused[FK_YZ_CI](&y, &z, &c, p->sms, st);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "fused inverse t0 (last part) launch (N=%d) failed: %s", e->N, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
+    }
     // backward X: src = [y_l][z][x] -> dst = [x][y_l][z] (chunked by destination device when chunk_base)
     static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base)
     {
@@ -1151,7 +1222,6 @@ template <typename T> struct Pass {
     }
 };
 
-static inline char* eoff(void* base, long long elems, size_t esz) { return (char*)base + (size_t)elems * esz; }
 
 // exchange offsets (api.cpp:84-133, 613-627): where chunk (sender s -> receiver r) starts
 static long long send_off(const Geom& g, int s, int r, int dir)
@@ -1349,6 +1419,80 @@ template <typename T> static int fwd_pipelined(dfft_plan p)
     return 0;
 }
 
+// Stream-pipelined backward transform (P > 1): the mirror image of fwd_pipelined.  Send side (plan stream): the inverse X
+// pass of z-part k, whose chunked store drops the x-planes of every destination straight into its receive buffer (P2P) or
+// into the part-major send buffer followed by ncclAlltoAll of the part (NCCL).  Receive side (second stream): as soon as part k
+// has arrived from every sender, the inverse Y pass of its columns (unpack folded into the load); the last part's Y pass
+// completes every plane and runs fused with the inverse Z pass.  Receive layout of device p, part k:
+// [sender q][x_l][y_l(q)][z'] at k * n0_l(p) * N1 * zk + q * n0_l(p) * yd * zk.
+template <typename T> static int bwd_pipelined(dfft_plan p)
+{
+    const Geom& g = p->g;
+    const int P = p->P, me = p->me, K = p->parts;
+    const long long zk = g.n2 / K;
+    const bool p2p = p->xmode == DFFT_EXCHANGE_P2P;
+    const bool scale = (p->flags & DFFT_SCALE_BACKWARD) != 0;
+    cudaStream_t A = p->stream, B = p->stream2, Cs = p->stream3;
+    int rc = 0;
+    struct Guard { dfft_plan p; ~Guard() { p->in_pipe = false; } } guard{p};
+    p->in_pipe = true;
+    int cap = 1;
+    if (getenv("DFFT_PIPE_CAP")) cap = atoi(getenv("DFFT_PIPE_CAP"));
+    if (p2p) {
+        p->epoch++;
+        if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;
+    }
+    CU(ev_record(p, p->pev[2][0]));
+    for (int k = 0; k < K; k++) {
+        void* base[DFFT_MAX_CHUNKS];
+        for (int q = 0; q < P; q++)
+            base[q] = p2p ? eoff(p->peer_work[q], ((long long)k * g.n1 + (long long)me * g.yd()) * g.n0l(q) * zk, p->esz)
+                          : eoff(p->sendbuf, ((long long)k * P + q) * g.xd() * p->n1l * zk, p->esz);
+        if ((rc = Pass<T>::xb_part(p, p->buf1, zk, k, base, k > 0 ? cap : 0))) return rc;
+        if (p2p) {
+            if (!p->done_ctr && (rc = flags_signal(p, 2 + k, p->epoch, A))) return rc;
+        } else {
+            const long long chunk = g.xd() * p->n1l * zk;
+            CU(ev_record_on(p, p->ev_y[k], A));
+            CU(stream_wait(p, Cs, p->ev_y[k]));
+            if ((rc = nccl_exchange_part(p, eoff(p->sendbuf, (long long)k * P * chunk, p->esz), eoff(p->work, (long long)k * P * chunk, p->esz), chunk, Cs))) return rc;
+            CU(ev_record_on(p, p->ev_a[k], Cs));
+        }
+    }
+    CU(ev_record(p, p->pev[2][1]));
+    CU(ev_record(p, p->ev[1]));
+    for (int k = 0; k < K; k++) {
+        if (p2p) { if ((rc = flags_wait(p, 2 + k, p->epoch, B))) return rc; }
+        else CU(stream_wait(p, B, p->ev_a[k]));
+        if (k == 0) CU(ev_record_on(p, p->pev[1][0], B));
+        if (k == K - 1) CU(ev_record_on(p, p->evb[0], B));
+        const void* rpart = eoff(p->work, (long long)k * p->n0l * g.n1 * zk, p->esz);
+        if (k == K - 1 && p->fuse) rc = Pass<T>::yz_fused_last_part(p, rpart, p->buf2, zk, k, scale, B);
+        else rc = Pass<T>::yinv_part(p, rpart, p->buf2, zk, k, k < K - 1 ? cap : 0, B);
+        if (rc) return rc;
+    }
+    CU(ev_record_on(p, p->pev[1][1], B));
+    if (!p->fuse) {
+        // inverse Z pass of the whole slab on the receive stream (Pass::z_pass launches on the plan stream: join first)
+        CU(ev_record_on(p, p->ev_join, B));
+        CU(stream_wait(p, A, p->ev_join));
+        if ((rc = Pass<T>::z_pass(p, p->buf2, p->buf2, scale))) return rc;
+        CU(ev_record(p, p->evb[1]));
+        CU(ev_record(p, p->pev[0][0])); CU(ev_record(p, p->pev[0][1]));
+        if (p2p && (rc = flags_signal(p, 0, p->epoch, A))) return rc;
+    } else {
+        CU(ev_record_on(p, p->pev[0][0], B)); CU(ev_record_on(p, p->pev[0][1], B));
+        CU(ev_record_on(p, p->evb[1], B));
+        if (p2p && (rc = flags_signal(p, 0, p->epoch, B))) return rc;
+        CU(ev_record_on(p, p->ev_join, B));
+        CU(stream_wait(p, A, p->ev_join));
+    }
+    CU(ev_record(p, p->ev[2]));
+    CU(ev_record(p, p->ev[3]));
+    p->timed = true;
+    return 0;
+}
+
 template <typename T> static int execute_fused(dfft_plan p)
 {
     const Geom& g = p->g;
@@ -1356,7 +1500,7 @@ template <typename T> static int execute_fused(dfft_plan p)
     int rc;
     p->launches = 0;
     CU(ev_record(p, p->ev[0]));
-    if (p->pipe) return fwd_pipelined<T>(p);
+    if (p->pipe) return p->direction == DFFT_FORWARD ? fwd_pipelined<T>(p) : bwd_pipelined<T>(p);
     if (p->direction == DFFT_FORWARD) {
         // t0 (+t1): Z pass out of place (bufferDev1 survives), Y pass with the pack (and, P2P, the
         // all-to-all) folded into its store
@@ -1555,7 +1699,8 @@ extern "C" int dfft_get_timings(dfft_plan p, double t[5])
         CU(cudaEventElapsedTime(&b, p->ev[1], p->evb[0]));
         CU(cudaEventElapsedTime(&c, p->evb[0], p->evb[1]));
         if (b < 0) { c += b; b = 0; }
-        t[0] = a; t[1] = 0; t[2] = b; t[3] = c;
+        if (p->direction == DFFT_FORWARD) { t[0] = a; t[1] = 0; t[2] = b; t[3] = c; }
+        else { t[3] = a; t[2] = b; t[1] = 0; t[0] = c; }   // backward: the send side is t3 (inverse X), the receive tail t0
     } else {
         float a, b, c;
         CU(cudaEventElapsedTime(&a, p->ev[0], p->ev[1]));

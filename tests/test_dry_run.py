@@ -217,6 +217,16 @@ def test_stream_pipelined_forward_schedule(co, monkeypatch, mode, P, n0, n1, n2,
     scale = max(np.abs(r).max() for r in ref)
     for d in range(P):
         assert np.abs(got[d][: g.out_count(d)] - ref[d][: g.out_count(d)]).max() <= 1e-11 * scale, d
+    # backward: inverse X parts (chunked to the destinations' part-major receive buffers), inverse Y parts (chunked load), the
+    # last one fused with the inverse Z pass when the planes are square
+    binputs, bref = oracle(co, g, A, BACKWARD)
+    bgot, bnames, _ = simulate(n0, n1, n2, P, BACKWARD, binputs, flags)
+    bscale = max(np.abs(r).max() for r in bref)
+    for d in range(P):
+        assert bnames[d].count("XB_CO") == K, bnames[d]
+        if mode == "nccl":
+            assert bnames[d].count("alltoall") == K
+        assert np.abs(bgot[d][: g.in_count(d)] - bref[d][: g.in_count(d)]).max() <= 1e-11 * bscale, (d, bnames[d])
     # DFFT_NO_PIPELINE falls back to the single-part schedule
     got2, names2, _ = simulate(n0, n1, n2, P, FORWARD, inputs, flags | dfft.NO_PIPELINE)
     assert names2[0].count("XF") == 1
