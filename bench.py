@@ -394,9 +394,11 @@ def run_dfft_arm(args):
         kernels = [("t0 fused Z+Y (fft_fused2_kernel: contiguous + strided role, intermediate L2-resident)", passes_avg[0], slab_bytes, 2 * slab_bytes, "t0_fused"),
                    ("X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)", passes_avg[2], slab_bytes, slab_bytes, "x")]
     else:
-        kernels = [("Z pass (contiguous, fft_tile_kernel MAP_T)", passes_avg[0], slab_bytes, slab_bytes, "z"),
-                   ("Y pass (strided + fused pack, fft_tile_kernel MAP_C)", passes_avg[1], slab_bytes, slab_bytes, "y"),
-                   ("X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)", passes_avg[2], slab_bytes, slab_bytes, "x")]
+        tm = plan.tma_mask
+        kn = lambda bit, tma, reg: tma if tm & bit else reg
+        kernels = [(kn(1, "Z pass (contiguous lines, fft_tma_pass_kernel TMA_Z: TMA ring)", "Z pass (contiguous, fft_tile_kernel MAP_T)"), passes_avg[0], slab_bytes, slab_bytes, kn(1, "z_tma", "z")),
+                   (kn(2, "Y pass (strided columns, fft_tma_pass_kernel TMA_Y: 3-D tensor TMA ring, in place)", "Y pass (strided + fused pack, fft_tile_kernel MAP_C)"), passes_avg[1], slab_bytes, slab_bytes, kn(2, "y_tma", "y")),
+                   (kn(4, "X pass (strided load + transposed store, fft_tma_pass_kernel TMA_XF)", "X pass (strided load + transposed store, fft_tile_kernel MAP_C->MAP_T)"), passes_avg[2], slab_bytes, slab_bytes, kn(4, "x_tma", "x"))]
     kname, kms, alg_bytes, conv_bytes, kkey = max(kernels, key=lambda k: k[1])
     achieved = alg_bytes / (kms * 1e-3) * 1e-9
     traffic = None

@@ -76,7 +76,7 @@ def lib():
     L.dfft_comm_allgather.argtypes = [vp, i, vp, vp, ctypes.c_size_t]
     L.dfft_exchange_table.argtypes = [ll, ll, ll, i, i, i, P(ll), P(ll), P(ll), P(ll)]
     L.dfft_plan_c2c_3d.argtypes = [ll, ll, ll, vp, vp, vp, i, i, i, i, u, P(vp)]
-    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused", "dfft_plan_pipeline_parts"):
+    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused", "dfft_plan_pipeline_parts", "dfft_plan_tma_mask"):
         getattr(L, name).argtypes = [vp]
     L.dfft_execute_stage.argtypes = [vp, i]
     L.dfft_execute_host.argtypes = [vp, vp, vp]
@@ -281,6 +281,11 @@ class Plan:
         buf = ctypes.create_string_buffer(int(n))
         lib().dfft_debug_plan_ops(self.handle, buf, n)
         return json.loads(buf.value.decode())
+
+    @property
+    def tma_mask(self):
+        """bit 0 / 1 / 2: the un-chunked Z / Y / X pass runs on the TMA-pipelined kernel"""
+        return lib().dfft_plan_tma_mask(self.handle)
 
     @property
     def pipeline_parts(self):

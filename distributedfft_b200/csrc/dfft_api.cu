@@ -1774,6 +1774,17 @@ extern "C" long long dfft_debug_plan_ops(dfft_plan p, char* buf, long long cap)
 
 extern "C" int dfft_plan_launches(dfft_plan p) { return p ? p->launches : 0; }
 extern "C" int dfft_plan_exchange(dfft_plan p) { return p ? p->xmode : 0; }
+/* bit 0 / 1 / 2: the un-chunked Z / Y / X pass of this plan runs on the TMA-pipelined kernel (fft_tma.cuh) */
+extern "C" int dfft_plan_tma_mask(dfft_plan p)
+{
+    if (!p || p->dry) return 0;
+    const Geom& g = p->g;
+    int m = 0;
+    if (p->tz && (p->tz->use & (1u << TMA_Z)) && (p->n0l * g.n1) % p->tz->C == 0) m |= 1;
+    if (p->ty && (p->ty->use & (1u << TMA_Y)) && g.n2 % p->ty->C == 0) m |= 2;
+    if (p->tx && (p->tx->use & (1u << (p->direction == DFFT_FORWARD ? TMA_XF : TMA_XB))) && g.n2 % p->tx->C == 0) m |= 4;
+    return m;
+}
 extern "C" int dfft_plan_pipeline_parts(dfft_plan p) { return p && p->pipe ? p->parts : 0; }
 extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? (p->overlap ? 2 : 1) : 0; }
 extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }

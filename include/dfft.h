@@ -179,7 +179,9 @@ int dfft_plan_launches(dfft_plan plan);
 /* 2: forward transform runs as the single overlapped kernel (DFFT_OVERLAP_X); 1: t0 runs as the fused two-pass
  * kernel (square planes, N1 == N2); 0: separate passes */
 int dfft_plan_fused(dfft_plan plan);
-/* number of z-parts of the stream-pipelined forward path, 0 when the plan does not use it */
+/* bit 0 / 1 / 2 set: the plan's un-chunked Z / Y / X pass runs on the TMA-pipelined kernel (fft_tma.cuh) */
+int dfft_plan_tma_mask(dfft_plan plan);
+/* number of z-parts of the stream-pipelined forward / backward path, 0 when the plan does not use it */
 int dfft_plan_pipeline_parts(dfft_plan plan);
 /* which exchange the plan resolved to (DFFT_EXCHANGE_*) */
 int dfft_plan_exchange(dfft_plan plan);
