@@ -373,9 +373,10 @@ __global__ void wait_flags_kernel(const unsigned long long* flags, int n, unsign
     const int q = threadIdx.x;
     if (q < n) {
         unsigned long long v;
+        SpinGuard guard;   // a peer that never signals (it died) traps this kernel after DFFT_SPIN_TIMEOUT_NS instead of hanging the GPU
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + q) : "memory");
-            if (v < value) __nanosleep(200);
+            if (v < value) { __nanosleep(200); guard.tick(); }
         } while (v < value);
     }
     __threadfence_system();

@@ -348,11 +348,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase)
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     return ok != 0;
 }
-// bounded wait: a transaction that never completes (bad size/alignment) traps instead of hanging the GPU
+// One timeout policy for every device-side wait (mbarrier, in-device plane counters, cross-device arrival flags): a wait
+// that has not been satisfied after DFFT_SPIN_TIMEOUT_NS of wall-clock time (%globaltimer) is a lost dependency -- a peer
+// that died, a transaction that can never complete -- and traps, so the host sees a launch failure instead of a GPU that
+// hangs forever.  The bound is far above any legitimate skew (process start-up, lazy module load, a peer's own waits).
+constexpr unsigned long long DFFT_SPIN_TIMEOUT_NS = 120ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long gtime_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct SpinGuard {
+    unsigned long long t0 = 0;
+    unsigned n = 0;
+    __device__ __forceinline__ void tick()
+    {
+        if ((++n & 1023u) == 0) {
+            const unsigned long long now = gtime_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > DFFT_SPIN_TIMEOUT_NS) __trap();
+        }
+    }
+};
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, phase); spins++)
-        if (spins > (1u << 26)) __trap();
+    SpinGuard g;
+    while (!mbar_try_wait(bar, phase)) g.tick();
 }
 __device__ __forceinline__ void fence_barrier_init()
 {

@@ -464,12 +464,12 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
         } else {
             if (threadIdx.x == 0) {
                 unsigned long long v;
-                unsigned spins = 0;
+                SpinGuard guard;
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(F.plane_done + plane) : "memory");
                     if (v >= F.target) break;
                     __nanosleep(64);
-                    if (++spins > (1u << 25)) __trap();   // a lost dependency traps instead of hanging the GPU
+                    guard.tick();   // a lost dependency traps (after DFFT_SPIN_TIMEOUT_NS) instead of hanging the GPU
                 }
             }
             __syncthreads();
@@ -609,12 +609,12 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
         } else if (role == 1) {
             if (threadIdx.x == 0) {
                 unsigned long long v;
-                unsigned spins = 0;
+                SpinGuard guard;
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(F.plane_done + plane) : "memory");
                     if (v >= F.target) break;
                     __nanosleep(64);
-                    if (++spins > (1u << 25)) __trap();
+                    guard.tick();
                 }
             }
             __syncthreads();
@@ -634,12 +634,12 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
             if (threadIdx.x < F.P) {
                 const unsigned long long* flag = F.my_arrive + (size_t)part * DFFT_MAX_CHUNKS + threadIdx.x;
                 unsigned long long v;
-                unsigned spins = 0;
+                SpinGuard guard;
                 for (;;) {
                     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
                     if (v >= F.epoch) break;
                     __nanosleep(128);
-                    if (++spins > (1u << 25)) __trap();
+                    guard.tick();
                 }
                 __threadfence_system();
             }
