@@ -68,6 +68,11 @@ inline dfft_comm& local_comm(int nranks)
     }
     return comm;
 }
+inline int& device_count()   // device count chosen by the last fft_mpi_init (what an MPI_Comm would tell the reference)
+{
+    static int n = 1;
+    return n;
+}
 }  // namespace dfft_shim
 
 inline longInt64 getMaxDataCount(int n0, int n1, int n2, int totalDevCount, bool isLastDevice)
@@ -83,6 +88,7 @@ inline void fft_mpi_init(const longInt64* N, int iniDeviceNumInNode, MPI_Comm, i
     for (int i = 0; i < newDeviceCountInNode; ++i)
         printf("data count in device %d of node %d: %lld\n", i, 0, dataCountInNode[i]);  /* api.cpp:285 */
     if (newDeviceCount > 1) dfft_shim::local_comm(newDeviceCount);
+    dfft_shim::device_count() = newDeviceCount;
 }
 
 inline void fft_mpi_cleanup(void) { dfft_cleanup(); }
@@ -91,6 +97,13 @@ inline longInt64 fft_mpi_local_size_3d(longInt64 n0, longInt64 n1, longInt64 n2,
                                        longInt64* local_n0, longInt64* local_0_start)
 {
     return dfft_local_size_3d(n0, n1, n2, totalDevCount, devIdx, local_n0, local_0_start, nullptr, nullptr);
+}
+
+/* the reference's own declaration (fft_mpi_3d_api.h:73; never defined there): the slab of the calling rank, i.e. of device
+ * 0 of the device count chosen by the last fft_mpi_init in this single-process build */
+inline longInt64 fft_mpi_local_size_3d(longInt64 n0, longInt64 n1, longInt64 n2, MPI_Comm, longInt64* local_n0, longInt64* local_0_start)
+{
+    return dfft_local_size_3d(n0, n1, n2, dfft_shim::device_count(), 0, local_n0, local_0_start, nullptr, nullptr);
 }
 
 inline Complex* fft_mpi_alloc_local_memory(longInt64 count, int flag)
