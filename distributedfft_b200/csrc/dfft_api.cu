@@ -703,9 +703,16 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
     {
         // stream-pipelined forward (z-parts): send side and receive side on two streams, see fwd_pipelined
         const char* env = getenv("DFFT_PIPELINE");
-        bool want = P > 1 && !p->overlap && (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_NCCL);
+        // Policy (profiles/r2_sweep_pipeline_*gpu.log): with 2 devices the transform is HBM-bound and already at ~95 % of its
+        // (6+2) E M roofline without any overlap, so cutting it into parts only adds launches and a second read of the
+        // intermediate (512^3: 1.38 ms plain, 1.43 / 1.53 ms with 2 / 4 parts); from 4 devices on the exchange is NVLink-bound
+        // and the receive-side X pass is what the pipeline hides.  NCCL collectives compete with the part kernels for SMs
+        // (2.47 ms plain vs 2.8-3.0 ms pipelined at 2 devices): opt-in there.  DFFT_FORCE_PIPELINE / DFFT_PIPELINE=1 override.
+        const bool possible = P > 1 && !p->overlap && (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_NCCL);
+        bool want = possible && xmode == DFFT_EXCHANGE_P2P && P >= 4;
+        if (env) want = possible && strcmp(env, "0") != 0;
+        if (flags & DFFT_FORCE_PIPELINE) want = possible;
         if (direction == DFFT_BACKWARD && getenv("DFFT_PIPELINE_BWD") && !strcmp(getenv("DFFT_PIPELINE_BWD"), "0")) want = false;
-        if (env) want = want && strcmp(env, "0") != 0;
         if (flags & DFFT_NO_PIPELINE) want = false;
         if (xmode == DFFT_EXCHANGE_NCCL && (n0 % P || n1 % P)) want = false;   // ncclAlltoAll parts need equal chunks
         if (want) {

@@ -60,11 +60,13 @@ extern "C" {
                                     the z axis is sent in parts and the X lines of a part start as soon as it has arrived
                                     from every sender, overlapping t3 with the NVLink-bound sends (env DFFT_OVERLAP=1) */
 
-#define DFFT_NO_PIPELINE 256u     /* forward, P > 1: do NOT cut the z axis into parts.  Default (P2P and NCCL exchanges): the send
-                                    side (Z, then per part the Y pass + pack + peer stores / ncclAlltoAll) and the receive side
-                                    (X pass of a part once it has arrived from every sender) run on two streams, so t2 and t3
-                                    overlap t0 -- the reference has no overlap at all (fft_mpi_3d_api.cpp:610-672).
-                                    env DFFT_PIPELINE=0 also disables it, DFFT_PARTS=k picks the number of parts */
+#define DFFT_NO_PIPELINE 256u     /* P > 1: do NOT cut the z axis into parts.  Stream-pipelined plans run the send side (Z, then per
+                                    part the Y pass + pack + peer stores / ncclAlltoAll; backward: inverse X parts) and the receive
+                                    side (X pass of a part once it has arrived from every sender; backward: inverse Y parts, inverse
+                                    Z) on two streams, so t2 and t3 overlap t0 -- the reference has no overlap at all
+                                    (fft_mpi_3d_api.cpp:610-672).  Default: P2P exchange with >= 4 devices.
+                                    env DFFT_PIPELINE=0 / 1 overrides, DFFT_PARTS=k picks the number of parts */
+#define DFFT_FORCE_PIPELINE 1024u /* stream-pipelined plan wherever it is possible (2 devices, NCCL exchange with equal chunks) */
 
 #define DFFT_NO_TMA 512u          /* use the register-staged pass kernels everywhere.  Default: passes whose load and store are both
                                     local and un-chunked (Z, natural Y, X) run on the TMA-pipelined kernels (fft_tma.cuh: 3-slot

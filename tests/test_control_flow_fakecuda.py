@@ -86,8 +86,8 @@ WORKER = textwrap.dedent(r'''
         for flags in (dfft.EXCHANGE_P2P, dfft.EXCHANGE_P2P | dfft.NO_FUSE, dfft.EXCHANGE_P2P | dfft.OVERLAP_X, dfft.EXCHANGE_STAGED):
             drive(64, 64, 64, P, flags)
             drive(12, 10, 24, P, flags)          # uneven split (short last slab), generic lengths
-        drive(8, 128, 128, P, dfft.EXCHANGE_P2P)     # stream-pipelined forward (4 z-parts, two streams), fused part 0
-        drive(8, 12, 128, P, dfft.EXCHANGE_P2P)      # ... two-sweep t0
+        drive(8, 128, 128, P, dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE)     # stream-pipelined (4 z-parts, two streams), fused part 0
+        drive(8, 12, 128, P, dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE)      # ... two-sweep t0
         drive(8, 128, 128, P, dfft.EXCHANGE_P2P | dfft.NO_PIPELINE)
     # the host-buffer entry points and the lines engine
     cnt = 16 * 16 * 16

@@ -203,7 +203,7 @@ def test_stream_pipelined_forward_schedule(co, monkeypatch, mode, P, n0, n1, n2,
     rng = np.random.default_rng(P + n2)
     A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
     inputs, ref = oracle(co, g, A, FORWARD)
-    flags = dfft.EXCHANGE_P2P if mode == "p2p" else dfft.EXCHANGE_NCCL
+    flags = (dfft.EXCHANGE_P2P if mode == "p2p" else dfft.EXCHANGE_NCCL) | dfft.FORCE_PIPELINE
     got, names, fused = simulate(n0, n1, n2, P, FORWARD, inputs, flags)
     K = int(parts) if parts else 4
     for d in range(P):
@@ -228,7 +228,7 @@ def test_stream_pipelined_forward_schedule(co, monkeypatch, mode, P, n0, n1, n2,
             assert bnames[d].count("alltoall") == K
         assert np.abs(bgot[d][: g.in_count(d)] - bref[d][: g.in_count(d)]).max() <= 1e-11 * bscale, (d, bnames[d])
     # DFFT_NO_PIPELINE falls back to the single-part schedule
-    got2, names2, _ = simulate(n0, n1, n2, P, FORWARD, inputs, flags | dfft.NO_PIPELINE)
+    got2, names2, _ = simulate(n0, n1, n2, P, FORWARD, inputs, (flags & ~dfft.FORCE_PIPELINE) | dfft.NO_PIPELINE)
     assert names2[0].count("XF") == 1
     for d in range(P):
         assert np.abs(got2[d][: g.out_count(d)] - ref[d][: g.out_count(d)]).max() <= 1e-11 * scale, d
