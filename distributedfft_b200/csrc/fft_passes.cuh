@@ -174,8 +174,7 @@ template <typename T>
 __device__ __forceinline__ void signal_when_grid_done(const TileArgs<T>& A)
 {
     if (A.sig_n <= 0) return;
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();          // the CTA's stores happen-before thread 0's fence (bar.sync), which is cumulative over them
     if (threadIdx.x == 0) {
         __threadfence_system();
         const unsigned prev = atomicAdd(A.done_ctr, 1u);
@@ -476,7 +475,7 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
             OpB::run(B, kb, plane * F.GB + idx, twb);
         }
     }
-    if (B.sig_n > 0) { __threadfence_system(); __syncthreads(); }   // this CTA's (peer) stores are ordered before it is counted
+    if (B.sig_n > 0) __syncthreads();   // this CTA's (peer) stores happen-before thread 0's cumulative system-scope fence
     if (threadIdx.x == 0) {
         if (B.sig_n > 0) __threadfence_system();
         const unsigned left = atomicAdd(F.ticket + 1, 1u);
@@ -498,8 +497,10 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
 // part 0 of every plane first (fused with the Z role through L2 as in fft_fused2_kernel), then parts 1..K-1;
 // as soon as part k has arrived from all P senders the X role can transform the (y_l, z in part k) lines, so
 // all but the last part of t3 runs while the NVLink-bound sends of later parts are still in flight.
-//   sender side : every finished Y tile of part k bumps part_done[k]; the tile that completes the part
-//                 publishes arrive[k][me] = epoch at every peer (fence.sys + st.release.sys)
+//   sender side : tickets are handed out in increasing order, so a CTA that draws a ticket beyond the Y tiles of part k has
+//                 stored its last tile of that part: it "passes" the part ONCE (bar.sync, then one fence.sys + atomicAdd by
+//                 thread 0 -- not a fence per tile, which serialises every tile behind an NVLink round trip); the CTA whose pass
+//                 completes the count publishes arrive[k][me] = epoch at every peer (st.release.sys)
 //   receiver    : an X tile of part k polls arrive[k][0..P) with ld.acquire.sys
 // Z and Y tiles never wait on a remote device, X tiles wait only on remote Y progress: no cross-device cycle;
 // inside the device the ticket order argument of fft_fused2_kernel applies unchanged.
@@ -509,9 +510,9 @@ constexpr int DFFT_MAX_PARTS = 8;
 struct Fused3Ctl {
     unsigned long long* plane_done;     // [planes]  Z-role completion per plane (monotonic)
     unsigned int* ticket;               // [0] next ticket, [1] CTAs that have left
-    unsigned long long* part_done;      // [K]       finished Y tiles per part (monotonic)
+    unsigned long long* part_done;      // [K]       CTAs that have passed the part (monotonic: epoch * gridDim.x when complete)
     unsigned long long target;          // plane_done value meaning "Z finished this plane in this execute"
-    unsigned long long part_target;     // part_done value meaning "every Y tile of the part is stored"
+    unsigned long long part_target;     // unused (the kernel derives the target from epoch and its grid size)
     unsigned long long epoch;           // value published in / awaited from the arrive flags
     const unsigned long long* my_arrive;                   // [K][DFFT_MAX_CHUNKS] on this device
     unsigned long long* peer_arrive[DFFT_MAX_CHUNKS];      // the same array on device q (peer mapped)
@@ -570,6 +571,17 @@ __host__ __device__ inline void fused3_decode(const Fused3Ctl& F, long long t, i
     else { role = 1; part = (int)ph + 1; plane = yi / F.GBk; idx = yi - plane * F.GBk; }
 }
 
+// lowest Y part whose tiles can still be handed out at tickets >= t (K when none can)
+__host__ __device__ inline int fused3_ypart_floor(const Fused3Ctl& F, long long t)
+{
+    const long long lag = F.lag < F.planes ? F.lag : F.planes;
+    const long long L0 = lag * F.GA + (F.planes - lag) * ((long long)F.GA + F.GBk) + lag * F.GBk;
+    if (t < L0) return 0;
+    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
+    const long long ph = (t - L0) / (LY + LX);
+    return ph < F.K - 1 ? (int)ph + 1 : F.K;
+}
+
 template <class OpA, class OpB, class OpC, typename T, int MINB>
 __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArgs<T> A, const TileArgs<T> B, const TileArgs<T> Cc, const Fused3Ctl F)
 {
@@ -590,11 +602,29 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
     OpC::load_twiddles(kc, twc);
 
     const long long total = fused3_total(F);
+    int passed = 0;              // Y parts this CTA has passed (uniform over the CTA)
+    // every thread's stores of the previous tile precede the bar.sync at the top of the loop, thread 0's system-scope fence
+    // after it is cumulative over them: one fence per CTA and part orders all of the CTA's peer stores of that part
+    auto pass_parts = [&](int upto) {
+        if (threadIdx.x == 0) {
+            for (int k = passed; k < upto; k++) {
+                __threadfence_system();
+                const unsigned long long old = atomicAdd(F.part_done + k, 1ull);
+                if (old + 1 == F.epoch * (unsigned long long)gridDim.x) {   // every CTA of this launch has passed part k
+                    __threadfence_system();
+                    for (int q = 0; q < F.P; q++)
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.peer_arrive[q] + (size_t)k * DFFT_MAX_CHUNKS + F.me), "l"(F.epoch) : "memory");
+                }
+            }
+        }
+        passed = upto > passed ? upto : passed;
+    };
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(F.ticket, 1u);
         __syncthreads();
         const long long t = s_ticket;
+        pass_parts(t >= total ? F.K : fused3_ypart_floor(F, t));
         if (t >= total) break;
         int role, part;          // role 0 = Z, 1 = Y, 2 = X
         long long plane, idx;    // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
@@ -619,17 +649,6 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
             }
             __syncthreads();
             OpB::run(B, kb, plane * F.GB + (long long)part * F.GBk + idx, twb);
-            __threadfence_system();                            // every thread orders its own peer stores at system scope ...
-            __syncthreads();                                   // ... before thread 0 counts the tile
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                const unsigned long long old = atomicAdd(F.part_done + part, 1ull);
-                if (old + 1 == F.part_target) {                // this tile completes the part on this device
-                    __threadfence_system();
-                    for (int q = 0; q < F.P; q++)
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.peer_arrive[q] + (size_t)part * DFFT_MAX_CHUNKS + F.me), "l"(F.epoch) : "memory");
-                }
-            }
         } else {
             if (threadIdx.x < F.P) {
                 const unsigned long long* flag = F.my_arrive + (size_t)part * DFFT_MAX_CHUNKS + threadIdx.x;
