@@ -603,6 +603,7 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
 
     const long long total = fused3_total(F);
     int passed = 0;              // Y parts this CTA has passed (uniform over the CTA)
+    unsigned arrived_mask = 0;   // parts whose arrival from every sender this CTA has already observed
     // every thread's stores of the previous tile precede the bar.sync at the top of the loop, thread 0's system-scope fence
     // after it is cumulative over them: one fence per CTA and part orders all of the CTA's peer stores of that part
     auto pass_parts = [&](int upto) {
@@ -650,19 +651,23 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
             __syncthreads();
             OpB::run(B, kb, plane * F.GB + (long long)part * F.GBk + idx, twb);
         } else {
-            if (threadIdx.x < F.P) {
-                const unsigned long long* flag = F.my_arrive + (size_t)part * DFFT_MAX_CHUNKS + threadIdx.x;
-                unsigned long long v;
-                SpinGuard guard;
-                for (;;) {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-                    if (v >= F.epoch) break;
-                    __nanosleep(128);
-                    guard.tick();
+            // the arrival of a part is polled once per CTA (arrived_mask, uniform): the acquire loads of threads 0..P-1 order
+            // the senders' stores before everything after the bar.sync; no fence is needed on this side
+            if (!((arrived_mask >> part) & 1u)) {
+                if (threadIdx.x < F.P) {
+                    const unsigned long long* flag = F.my_arrive + (size_t)part * DFFT_MAX_CHUNKS + threadIdx.x;
+                    unsigned long long v;
+                    SpinGuard guard;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+                        if (v >= F.epoch) break;
+                        __nanosleep(128);
+                        guard.tick();
+                    }
                 }
-                __threadfence_system();
+                arrived_mask |= 1u << part;
+                __syncthreads();
             }
-            __syncthreads();
             const long long row = idx / F.GXk, bb = idx - row * F.GXk;
             OpC::run(Cc, kc, row * F.GX + (long long)part * F.GXk + bb, twc);
         }
