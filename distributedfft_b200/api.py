@@ -105,6 +105,7 @@ def lib():
     L.dfft_debug_fused3_order.argtypes = [ll, ll, i, i, i, i, i, ll, P(ll)]
     L.dfft_debug_fused3_order.restype = ll
     L.dfft_memcpy.argtypes = [vp, vp, ctypes.c_size_t, i]
+    L.dfft_debug_timeline.argtypes = [vp, P(ctypes.c_double)]
     _lib = L
     return L
 
@@ -282,6 +283,11 @@ class Plan:
         buf = ctypes.create_string_buffer(int(n))
         lib().dfft_debug_plan_ops(self.handle, buf, n)
         return json.loads(buf.value.decode())
+
+    def debug_timeline(self):
+        t = (ctypes.c_double * 11)()
+        _check(lib().dfft_debug_timeline(self.handle, t), "dfft_debug_timeline")
+        return list(t)
 
     @property
     def tma_mask(self):

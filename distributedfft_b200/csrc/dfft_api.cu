@@ -442,6 +442,7 @@ struct dfft_plan_s {
     cudaEvent_t ev_join = nullptr, evb[2] = {nullptr, nullptr};
     cudaEvent_t ev_y[DFFT_MAX_PARTS] = {}, ev_a[DFFT_MAX_PARTS] = {};
     void* sendbuf = nullptr;         // NCCL: part-major packed send buffer
+    unsigned long long* dbg = nullptr;   // DFFT_DEBUG_TIMELINE: device-side timeline of the single-kernel forward path
     unsigned int* done_ctr = nullptr; // [DFFT_MAX_PARTS] finished-CTA counters of the part kernels (arrival signal folded into the kernel)
 };
 
@@ -808,6 +809,7 @@ extern "C" int dfft_destroy(dfft_plan p)
     if (p->mid) cudaFree(p->mid);
     if (p->sendbuf) cudaFree(p->sendbuf);
     if (p->done_ctr) cudaFree(p->done_ctr);
+    if (p->dbg) cudaFree(p->dbg);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (auto& e : p->evb) if (e) cudaEventDestroy(e);
     for (auto& e : p->ev_y) if (e) cudaEventDestroy(e);
@@ -1016,6 +1018,13 @@ template <typename T> struct Pass {
             for (int q = 0; q < p->P; q++) c.peer_arrive[q] = &p->peer_sync[q]->part_arrive[0][0];
         }
         c.lag = p->lag;
+        c.dbg = nullptr;
+        if (!p->dry && getenv("DFFT_DEBUG_TIMELINE")) {
+            if (!p->dbg) cudaMalloc((void**)&p->dbg, 16 * sizeof(unsigned long long));
+            cudaMemsetAsync(p->dbg, 0xff, 4 * sizeof(unsigned long long), p->stream);
+            cudaMemsetAsync(p->dbg + 4, 0, 12 * sizeof(unsigned long long), p->stream);
+            c.dbg = p->dbg;
+        }
         if (p->dry) {
             record_op<T>(p, "ovlZ", 0, e->N, CZ, false, false, false, z);
             record_op<T>(p, "ovlY", 0, e->N, CY, false, true, false, y);
@@ -1792,6 +1801,23 @@ extern "C" int dfft_plan_tma_mask(dfft_plan p)
     if (p->ty && (p->ty->use & (1u << TMA_Y)) && g.n2 % p->ty->C == 0) m |= 2;
     if (p->tx && (p->tx->use & (1u << (p->direction == DFFT_FORWARD ? TMA_XF : TMA_XB))) && g.n2 % p->tx->C == 0) m |= 4;
     return m;
+}
+/* developer hook (DFFT_DEBUG_TIMELINE=1, single-kernel forward path): device-side timeline of the last execute, microseconds
+ * relative to the kernel's start: [0] end of phase 0, [1] first X tile, [2] kernel end, [3..5] mean us per Z / Y / X tile,
+ * [6..8] tile counts, [9] mean X-side wait per CTA, [10] max wait */
+extern "C" int dfft_debug_timeline(dfft_plan p, double out[11])
+{
+    if (!p || !p->dbg || !out) return fail(DFFT_EINVAL, "no timeline recorded (set DFFT_DEBUG_TIMELINE=1 and use DFFT_OVERLAP_X)");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    unsigned long long h[16];
+    CU(cudaMemcpy(h, p->dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    const double t0 = (double)h[0];
+    out[0] = ((double)h[4] - t0) * 1e-3; out[1] = ((double)h[1] - t0) * 1e-3; out[2] = ((double)h[5] - t0) * 1e-3;
+    for (int r = 0; r < 3; r++) { out[3 + r] = h[9 + r] ? (double)h[6 + r] / (double)h[9 + r] * 1e-3 : 0; out[6 + r] = (double)h[9 + r]; }
+    const double ctas = (double)p->sms * 2;
+    out[9] = (double)h[12] / ctas * 1e-3; out[10] = (double)h[13] * 1e-3;
+    return 0;
 }
 extern "C" int dfft_plan_pipeline_parts(dfft_plan p) { return p && p->pipe ? p->parts : 0; }
 extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? (p->overlap ? 2 : 1) : 0; }

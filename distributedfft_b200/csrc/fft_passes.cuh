@@ -520,6 +520,8 @@ struct Fused3Ctl {
     int P, me;
     int GA, GB, GBk, GX, GXk, K;        // tiles per plane (Z, Y), Y tiles per plane and part, X tiles per row (all, per part), parts
     int lag;
+    // optional timeline (DFFT_DEBUG_TIMELINE): dbg[0..3] minima (start, first X tile), dbg[4..15] maxima / sums, all in ns of %globaltimer
+    unsigned long long* dbg;
 };
 
 // Ticket order of fft_fused3_kernel (host-callable so that the CPU tests can check it is a bijection onto the tiles
@@ -602,6 +604,10 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
     OpC::load_twiddles(kc, twc);
 
     const long long total = fused3_total(F);
+    unsigned long long dbg_t[3] = {0, 0, 0}, dbg_wait = 0, dbg_prev = 0;
+    int dbg_n[3] = {0, 0, 0};
+    bool dbg_first_x = true, dbg_phase0_done = false;
+    if (F.dbg && threadIdx.x == 0) { dbg_prev = gtime_ns(); atomicMin(F.dbg + 0, dbg_prev); }
     int passed = 0;              // Y parts this CTA has passed (uniform over the CTA)
     unsigned arrived_mask = 0;   // parts whose arrival from every sender this CTA has already observed
     // every thread's stores of the previous tile precede the bar.sync at the top of the loop, thread 0's system-scope fence
@@ -626,10 +632,15 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
         __syncthreads();
         const long long t = s_ticket;
         pass_parts(t >= total ? F.K : fused3_ypart_floor(F, t));
+        if (F.dbg && threadIdx.x == 0 && !dbg_phase0_done && (t >= total || fused3_ypart_floor(F, t) > 0)) {
+            dbg_phase0_done = true;
+            atomicMax(F.dbg + 4, gtime_ns());      // end of phase 0 (Z + Y part 0) on this device
+        }
         if (t >= total) break;
         int role, part;          // role 0 = Z, 1 = Y, 2 = X
         long long plane, idx;    // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
         fused3_decode(F, t, role, part, plane, idx);
+        if (F.dbg && threadIdx.x == 0) dbg_prev = gtime_ns();
         if (role == 0) {
             OpA::run(A, ka, plane * F.GA + idx, twa);
             __syncthreads();
@@ -667,10 +678,19 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
                 }
                 arrived_mask |= 1u << part;
                 __syncthreads();
+                if (F.dbg && threadIdx.x == 0) { const unsigned long long now = gtime_ns(); dbg_wait += now - dbg_prev; dbg_prev = now; }
             }
+            if (F.dbg && threadIdx.x == 0 && dbg_first_x) { dbg_first_x = false; atomicMin(F.dbg + 1, gtime_ns()); }
             const long long row = idx / F.GXk, bb = idx - row * F.GXk;
             OpC::run(Cc, kc, row * F.GX + (long long)part * F.GXk + bb, twc);
         }
+        if (F.dbg && threadIdx.x == 0) { dbg_t[role] += gtime_ns() - dbg_prev; dbg_n[role]++; }
+    }
+    if (F.dbg && threadIdx.x == 0) {
+        atomicMax(F.dbg + 5, gtime_ns());          // kernel end
+        for (int r = 0; r < 3; r++) { atomicAdd(F.dbg + 6 + r, dbg_t[r]); atomicAdd(F.dbg + 9 + r, (unsigned long long)dbg_n[r]); }
+        atomicAdd(F.dbg + 12, dbg_wait);
+        atomicMax(F.dbg + 13, dbg_wait);
     }
     if (threadIdx.x == 0) {
         const unsigned left = atomicAdd(F.ticket + 1, 1u);

@@ -68,6 +68,9 @@ for item in sys.argv[1:]:
         ms, pt, st = t[0].item(), t[1:4].tolist(), t[4:].tolist()
     if rank == 0:
         print(f"{item:60s} P={world} fused={int(plan.fused)} parts={plan.pipeline_parts} ms/step {ms:8.4f}  pass {[round(x, 4) for x in pt]}  stage {[round(x, 4) for x in st[:4]]}", flush=True)
+    if os.environ.get("DFFT_DEBUG_TIMELINE") and plan.overlapped:
+        tl = plan.debug_timeline()
+        print(f"   rank {rank} timeline us: phase0_end {tl[0]:.1f} first_X {tl[1]:.1f} end {tl[2]:.1f} | us/tile Z {tl[3]:.2f} Y {tl[4]:.2f} X {tl[5]:.2f} | tiles {tl[6]:.0f} {tl[7]:.0f} {tl[8]:.0f} | wait mean {tl[9]:.1f} max {tl[10]:.1f}", flush=True)
     plan.destroy()
     del tin, tout
     torch.cuda.empty_cache()

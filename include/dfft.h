@@ -183,6 +183,9 @@ int dfft_plan_launches(dfft_plan plan);
 int dfft_plan_fused(dfft_plan plan);
 /* bit 0 / 1 / 2 set: the plan's un-chunked Z / Y / X pass runs on the TMA-pipelined kernel (fft_tma.cuh) */
 int dfft_plan_tma_mask(dfft_plan plan);
+/* developer hook: device-side timeline of the last execute of a DFFT_OVERLAP_X plan created under DFFT_DEBUG_TIMELINE=1 (microseconds
+ * from kernel start: end of phase 0, first X tile, kernel end; mean us per Z / Y / X tile; tile counts; mean / max arrival wait) */
+int dfft_debug_timeline(dfft_plan plan, double out[11]);
 /* number of z-parts of the stream-pipelined forward / backward path, 0 when the plan does not use it */
 int dfft_plan_pipeline_parts(dfft_plan plan);
 /* which exchange the plan resolved to (DFFT_EXCHANGE_*) */

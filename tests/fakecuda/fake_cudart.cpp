@@ -71,6 +71,7 @@ cudaError_t cudaFreeHost(void* p) { if (p) g_frees++; free(p); return 0; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { if (d != s) memmove(d, s, n); return 0; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { if (d != s) memmove(d, s, n); return 0; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_st* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return 0; }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_st h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return 0; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
