@@ -75,11 +75,12 @@ extern "C" long long dfft_debug_fused3_order(long long planes, long long rows, i
 {
     Fused3Ctl F{};
     F.planes = planes; F.rows = rows; F.GA = GA; F.GBk = GBk; F.GB = GBk * K; F.GXk = GXk; F.GX = GXk * K; F.K = K; F.lag = lag;
-    const long long total = fused3_total(F);
+    const Fused3Order o = fused3_prepare(F);
+    const long long total = (long long)o.total;
     if (ticket < 0 || ticket >= total || !out) return total;
-    int role, part;
-    long long plane, idx;
-    fused3_decode(F, ticket, role, part, plane, idx);
+    int role, part, yfloor;
+    unsigned plane, idx;
+    fused3_decode(F, o, (unsigned)ticket, role, part, plane, idx, yfloor);
     out[0] = role; out[1] = part; out[2] = plane; out[3] = idx;
     return total;
 }

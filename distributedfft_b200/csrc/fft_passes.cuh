@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
             roleA = false; plane = F.planes - lag + i; idx = u - i * F.GB;
         }
         if (roleA) {
-            OpA::run(A, ka, plane * F.GA + idx, twa);
+            OpA::run(A, ka, (long long)plane * F.GA + idx, twa);
             __syncthreads();                       // every thread's stores are issued ...
             if (threadIdx.x == 0) {
                 __threadfence();                   // ... and ordered before the release
@@ -525,63 +525,79 @@ struct Fused3Ctl {
 };
 
 // Ticket order of fft_fused3_kernel (host-callable so that the CPU tests can check it is a bijection onto the tiles
-// and respects the dependency order):
+// and respects the dependency order).  All arithmetic is 32-bit with a handful of divisions: a ticket is decoded by every
+// CTA for every tile, and the first version's 64-bit proportional interleave cost about a microsecond per ticket.
 //   phase 0        : Z on every plane + Y part 0, interleaved like fft_fused2_kernel (Z runs `lag` planes ahead)
-//   phase k = 1..K-1: Y part k (LY tiles, plane-major) merged with X part k-1 (LX tiles); the X tiles start after a
-//                    quarter of the phase's Y tiles and are then spread evenly
+//   phase k = 1..K-1: Y part k (LY tiles, plane-major) merged with X part k-1 (LX tiles): first `dly` Y tiles (the part has to
+//                    arrive from the peers before its X tiles can run), then blocks of blkA X tiles + blkB Y tiles, then
+//                    whatever is left of either kind
 //   tail           : X part K-1
-__host__ __device__ inline long long fused3_total(const Fused3Ctl& F)
+// fused3_prepare derives the constants (cheap; once per CTA).
+struct Fused3Order {
+    unsigned lagp, headT, midT, L0, per0, LY, LX, dly, blkA, blkB, nblk, mixT, phaseT, total;
+};
+__host__ __device__ inline Fused3Order fused3_prepare(const Fused3Ctl& F)
 {
-    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
-    return F.planes * ((long long)F.GA + F.GBk) + (long long)(F.K - 1) * (LY + LX) + LX;
+    Fused3Order o{};
+    o.lagp = (unsigned)(F.lag < F.planes ? F.lag : F.planes);
+    o.per0 = (unsigned)(F.GA + F.GBk);
+    o.headT = o.lagp * (unsigned)F.GA;
+    o.midT = ((unsigned)F.planes - o.lagp) * o.per0;
+    o.L0 = o.headT + o.midT + o.lagp * (unsigned)F.GBk;
+    o.LY = (unsigned)F.planes * (unsigned)F.GBk;
+    o.LX = (unsigned)F.rows * (unsigned)F.GXk;
+    o.dly = o.LY / 4;
+    const unsigned ym = o.LY - o.dly;
+    // block shape: blkA : blkB ~ LX : ym with blkA + blkB = 8
+    unsigned a = ym + o.LX ? (unsigned)((8ull * o.LX + (ym + o.LX) / 2) / (ym + o.LX)) : 4;
+    a = a < 1 ? 1 : (a > 7 ? 7 : a);
+    o.blkA = a; o.blkB = 8 - a;
+    const unsigned nx = o.LX / o.blkA, ny = ym / o.blkB;
+    o.nblk = nx < ny ? nx : ny;
+    o.mixT = o.nblk * 8u;
+    o.phaseT = o.LY + o.LX;
+    o.total = o.L0 + (unsigned)(F.K - 1) * o.phaseT + o.LX;
+    return o;
 }
-__host__ __device__ inline void fused3_decode(const Fused3Ctl& F, long long t, int& role, int& part, long long& plane, long long& idx)
+__host__ __device__ inline long long fused3_total(const Fused3Ctl& F) { return (long long)fused3_prepare(F).total; }
+// role 0 = Z, 1 = Y, 2 = X; ypart_floor = lowest Y part whose tiles can still be handed out at tickets >= t
+__host__ __device__ inline void fused3_decode(const Fused3Ctl& F, const Fused3Order& o, unsigned t, int& role, int& part, unsigned& plane, unsigned& idx,
+                                              int& ypart_floor)
 {
-    const long long lag = F.lag < F.planes ? F.lag : F.planes;
-    const long long headT = lag * F.GA;
-    const long long midT = (F.planes - lag) * ((long long)F.GA + F.GBk);
-    const long long L0 = headT + midT + lag * F.GBk;
-    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
-    const long long dly = LY / 4, LM = LY - dly + LX;
     part = 0; plane = 0; idx = 0;
-    if (t < L0) {
-        if (t < headT) { role = 0; plane = t / F.GA; idx = t - plane * F.GA; }
-        else if (t < headT + midT) {
-            const long long u = t - headT, i = u / (F.GA + F.GBk), r = u - i * (F.GA + F.GBk);
-            if (r < F.GA) { role = 0; plane = lag + i; idx = r; }
-            else { role = 1; plane = i; idx = r - F.GA; }
+    if (t < o.L0) {
+        ypart_floor = 0;
+        if (t < o.headT) { role = 0; plane = t / (unsigned)F.GA; idx = t - plane * (unsigned)F.GA; }
+        else if (t < o.headT + o.midT) {
+            const unsigned u = t - o.headT, i = u / o.per0, r = u - i * o.per0;
+            if (r < (unsigned)F.GA) { role = 0; plane = o.lagp + i; idx = r; }
+            else { role = 1; plane = i; idx = r - (unsigned)F.GA; }
         } else {
-            const long long u = t - headT - midT, i = u / F.GBk;
-            role = 1; plane = F.planes - lag + i; idx = u - i * F.GBk;
+            const unsigned u = t - o.headT - o.midT, i = u / (unsigned)F.GBk;
+            role = 1; plane = (unsigned)F.planes - o.lagp + i; idx = u - i * (unsigned)F.GBk;
         }
         return;
     }
-    const long long u0 = t - L0;
-    const long long ph = u0 / (LY + LX);          // 0-based: phase ph+1, or >= K-1 for the final X part
-    const long long u = u0 - ph * (LY + LX);
-    if (ph >= F.K - 1) { role = 2; part = F.K - 1; idx = u; return; }
-    long long yi;
+    const unsigned u0 = t - o.L0, ph = u0 / o.phaseT, u = u0 - ph * o.phaseT;
+    if (ph >= (unsigned)(F.K - 1)) { role = 2; part = F.K - 1; idx = u; ypart_floor = F.K; return; }
+    ypart_floor = (int)ph + 1;
+    unsigned yi;
     bool isx = false;
-    if (u < dly) yi = u;
+    if (u < o.dly) yi = u;
     else {
-        const long long v = u - dly;
-        const long long xc0 = v * LX / LM, xc1 = (v + 1) * LX / LM;   // X tiles placed before position v / v+1
-        if (xc1 > xc0) { isx = true; yi = xc0; }
-        else yi = dly + v - xc0;
+        const unsigned v = u - o.dly;
+        if (v < o.mixT) {
+            const unsigned q = v >> 3, r = v & 7u;
+            if (r < o.blkA) { isx = true; yi = q * o.blkA + r; }
+            else yi = o.dly + q * o.blkB + (r - o.blkA);
+        } else {
+            const unsigned w = v - o.mixT, remx = o.LX - o.nblk * o.blkA;
+            if (w < remx) { isx = true; yi = o.nblk * o.blkA + w; }
+            else yi = o.dly + o.nblk * o.blkB + (w - remx);
+        }
     }
     if (isx) { role = 2; part = (int)ph; idx = yi; }
-    else { role = 1; part = (int)ph + 1; plane = yi / F.GBk; idx = yi - plane * F.GBk; }
-}
-
-// lowest Y part whose tiles can still be handed out at tickets >= t (K when none can)
-__host__ __device__ inline int fused3_ypart_floor(const Fused3Ctl& F, long long t)
-{
-    const long long lag = F.lag < F.planes ? F.lag : F.planes;
-    const long long L0 = lag * F.GA + (F.planes - lag) * ((long long)F.GA + F.GBk) + lag * F.GBk;
-    if (t < L0) return 0;
-    const long long LY = F.planes * F.GBk, LX = F.rows * F.GXk;
-    const long long ph = (t - L0) / (LY + LX);
-    return ph < F.K - 1 ? (int)ph + 1 : F.K;
+    else { role = 1; part = (int)ph + 1; plane = yi / (unsigned)F.GBk; idx = yi - plane * (unsigned)F.GBk; }
 }
 
 template <class OpA, class OpB, class OpC, typename T, int MINB>
@@ -603,7 +619,8 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
     OpB::load_twiddles(kb, twb);
     OpC::load_twiddles(kc, twc);
 
-    const long long total = fused3_total(F);
+    const Fused3Order ord = fused3_prepare(F);
+    const long long total = (long long)ord.total;
     unsigned long long dbg_t[3] = {0, 0, 0}, dbg_wait = 0, dbg_prev = 0;
     int dbg_n[3] = {0, 0, 0};
     bool dbg_first_x = true, dbg_phase0_done = false;
@@ -631,18 +648,18 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
         if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(F.ticket, 1u);
         __syncthreads();
         const long long t = s_ticket;
-        pass_parts(t >= total ? F.K : fused3_ypart_floor(F, t));
-        if (F.dbg && threadIdx.x == 0 && !dbg_phase0_done && (t >= total || fused3_ypart_floor(F, t) > 0)) {
+        int role = 0, part = 0, yfloor = F.K;   // role 0 = Z, 1 = Y, 2 = X
+        unsigned plane = 0, idx = 0;            // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
+        if (t < total) fused3_decode(F, ord, (unsigned)t, role, part, plane, idx, yfloor);
+        pass_parts(yfloor);
+        if (F.dbg && threadIdx.x == 0 && !dbg_phase0_done && yfloor > 0) {
             dbg_phase0_done = true;
             atomicMax(F.dbg + 4, gtime_ns());      // end of phase 0 (Z + Y part 0) on this device
         }
         if (t >= total) break;
-        int role, part;          // role 0 = Z, 1 = Y, 2 = X
-        long long plane, idx;    // Z/Y: plane + tile within (plane[, part]); X: idx = tile within the part
-        fused3_decode(F, t, role, part, plane, idx);
         if (F.dbg && threadIdx.x == 0) dbg_prev = gtime_ns();
         if (role == 0) {
-            OpA::run(A, ka, plane * F.GA + idx, twa);
+            OpA::run(A, ka, (long long)plane * F.GA + idx, twa);
             __syncthreads();
             if (threadIdx.x == 0) {
                 __threadfence();
@@ -660,7 +677,7 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
                 }
             }
             __syncthreads();
-            OpB::run(B, kb, plane * F.GB + (long long)part * F.GBk + idx, twb);
+            OpB::run(B, kb, (long long)plane * F.GB + (long long)part * F.GBk + idx, twb);
         } else {
             // the arrival of a part is polled once per CTA (arrived_mask, uniform): the acquire loads of threads 0..P-1 order
             // the senders' stores before everything after the bar.sync; no fence is needed on this side
@@ -681,8 +698,8 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused3_kernel(const TileArg
                 if (F.dbg && threadIdx.x == 0) { const unsigned long long now = gtime_ns(); dbg_wait += now - dbg_prev; dbg_prev = now; }
             }
             if (F.dbg && threadIdx.x == 0 && dbg_first_x) { dbg_first_x = false; atomicMin(F.dbg + 1, gtime_ns()); }
-            const long long row = idx / F.GXk, bb = idx - row * F.GXk;
-            OpC::run(Cc, kc, row * F.GX + (long long)part * F.GXk + bb, twc);
+            const unsigned row = idx / (unsigned)F.GXk, bb = idx - row * (unsigned)F.GXk;
+            OpC::run(Cc, kc, (long long)row * F.GX + (long long)part * F.GXk + bb, twc);
         }
         if (F.dbg && threadIdx.x == 0) { dbg_t[role] += gtime_ns() - dbg_prev; dbg_n[role]++; }
     }
