@@ -77,7 +77,7 @@ def lib():
     L.dfft_comm_allgather.argtypes = [vp, i, vp, vp, ctypes.c_size_t]
     L.dfft_exchange_table.argtypes = [ll, ll, ll, i, i, i, P(ll), P(ll), P(ll), P(ll)]
     L.dfft_plan_c2c_3d.argtypes = [ll, ll, ll, vp, vp, vp, i, i, i, i, u, P(vp)]
-    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused", "dfft_plan_pipeline_parts", "dfft_plan_tma_mask"):
+    for name in ("dfft_execute", "dfft_synchronize", "dfft_destroy", "dfft_plan_launches", "dfft_plan_exchange", "dfft_plan_fused", "dfft_plan_pipeline_parts", "dfft_plan_tma_mask", "dfft_plan_pipeline_chain"):
         getattr(L, name).argtypes = [vp]
     L.dfft_execute_stage.argtypes = [vp, i]
     L.dfft_execute_host.argtypes = [vp, vp, vp]
@@ -298,6 +298,11 @@ class Plan:
     def pipeline_parts(self):
         """z-parts of the stream-pipelined forward path (0 = not pipelined)"""
         return lib().dfft_plan_pipeline_parts(self.handle)
+
+    @property
+    def pipeline_chain(self):
+        """the z-parts run as a chain of two-role kernels on one stream (Y part k + X part k-1 per kernel)"""
+        return bool(lib().dfft_plan_pipeline_chain(self.handle))
 
     @property
     def overlapped(self):

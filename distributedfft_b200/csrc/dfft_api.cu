@@ -438,6 +438,8 @@ struct dfft_plan_s {
     // part k with the pack / peer stores folded in, or + ncclAlltoAll of part k on the comm stream) runs ahead of the receive
     // side (stream2: X pass of part k as soon as part k has arrived from every sender) -- t2 and t3 overlap t0
     bool pipe = false;
+    bool pipe_fyx = false;           // forward, cube, P2P: parts run as a chain of two-role kernels on ONE stream (fft_fused_yx_kernel:
+                                     // Y pass of part k + X pass of part k-1 share every SM slot) instead of two streams
     bool in_pipe = false;            // inside fwd_pipelined: Pass::launch leaves the per-pass event brackets alone
     cudaStream_t stream2 = nullptr, stream3 = nullptr;   // receive side; NCCL part exchanges
     cudaEvent_t ev_join = nullptr, evb[2] = {nullptr, nullptr};
@@ -732,6 +734,11 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
             if (K >= 1 && (K > 1 || getenv("DFFT_PARTS"))) {
                 p->parts = K;
                 p->pipe = true;
+                {
+                    const char* pm = getenv("DFFT_PIPE_MODE");   // "streams": the two-stream schedule even where the kernel chain is possible
+                    p->pipe_fyx = direction == DFFT_FORWARD && xmode == DFFT_EXCHANGE_P2P && p->fuse && ey == ex && ey->fused_yx != nullptr &&
+                                  !(pm && !strcmp(pm, "streams"));
+                }
                 if (dry) { p->mid = fake_addr(dev_idx, 4); p->sendbuf = fake_addr(dev_idx, 6); }
                 else {
                     if (!p->mid && direction == DFFT_FORWARD) CUP(cudaMalloc(&p->mid, (size_t)p->max_count * p->esz));
@@ -1126,6 +1133,38 @@ template <typename T> struct Pass {
         return 0;
     }
     // X pass of one z-part on the receive side: rpart = [x (all N0)][y_l][z'] (row length zk) -> dst[y_l][z in part][x]
+    static void x_part_args(dfft_plan p, TileArgs<T>& a, const void* rpart, void* dst, long long zk, int k)
+    {
+        const Geom& g = p->g;
+        const int C = p->ex->x_C;
+        a.in = (const cx<T>*)rpart; a.out = (cx<T>*)dst + k * zk * g.n0; a.lut = (const cx<T>*)p->lut_x;
+        a.G = (int)cdiv(zk, C); a.W = (int)zk; a.ntiles = p->n1l * a.G;
+        a.ia = Affine{zk, C, 1, p->n1l * zk};
+        a.oa = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
+    }
+    // Y pass of part k (stores to the peers) and X pass of part k-1 (already arrived) in one two-role kernel
+    static int yx_fused(dfft_plan p, const void* mid, long long zk, int k, void* const* chunk_base, const void* rpart_prev, void* dst)
+    {
+        const SizeEntry* e = p->ey;
+        TileArgs<T> y{}, x{};
+        y_part_args(p, y, mid, zk, k, chunk_base, e->p_C);
+        x_part_args(p, x, rpart_prev, dst, zk, k - 1);
+        YxCtl c{};
+        c.ticket = p->ticket;
+        c.my_arrive = p->dry ? nullptr : &p->sync->part_arrive[k - 1][0];
+        c.epoch = p->epoch; c.P = p->P;
+        c.TA = (unsigned)y.ntiles; c.TB = (unsigned)x.ntiles;
+        if (p->dry) {
+            record_op<T>(p, "Y_CO", 0, e->N, e->p_C, false, true, false, y);
+            record_op<T>(p, "XF", 1, e->N, e->x_C, false, false, true, x);
+            p->launches++;
+            return 0;
+        }
+        cudaError_t err = e->fused_yx(&y, &x, &c, p->sms, p->stream);
+        if (err != cudaSuccess) return fail(DFFT_ECUDA, "fused Y+X part launch (N=%d, part %d) failed: %s", e->N, k, cudaGetErrorString(err));
+        p->launches++;
+        return 0;
+    }
     static int x_part(dfft_plan p, const void* rpart, void* dst, long long zk, int k, int cap, cudaStream_t st)
     {
         const Geom& g = p->g;
@@ -1394,6 +1433,31 @@ template <typename T> static int fwd_pipelined(dfft_plan p)
         if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
     }
     CU(ev_record(p, p->pev[0][0]));
+    if (p->pipe_fyx) {
+        // chain of two-role kernels on the plan stream: [Z + Y part 0] [Y part 1 + X part 0] ... [Y part K-1 + X part K-2] [X part K-1]
+        for (int k = 0; k < K; k++) {
+            void* base[DFFT_MAX_CHUNKS];
+            for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], ((long long)k * g.n0 + (long long)me * g.xd()) * g.n1l(q) * zk, p->esz);
+            if (k == 0) rc = Pass<T>::zy_fused_part0(p, p->buf1, p->mid, zk, base);
+            else rc = Pass<T>::yx_fused(p, p->mid, zk, k, base, eoff(p->work, (long long)(k - 1) * g.n0 * p->n1l * zk, p->esz), p->buf2);
+            if (rc) return rc;
+            if (!p->done_ctr && (rc = flags_signal(p, 2 + k, p->epoch, A))) return rc;   // else the kernel's last CTA publishes the flags
+        }
+        CU(ev_record(p, p->pev[0][1]));
+        CU(ev_record(p, p->pev[1][0])); CU(ev_record(p, p->pev[1][1]));
+        CU(ev_record(p, p->ev[1]));
+        if ((rc = flags_wait(p, 2 + K - 1, p->epoch, A))) return rc;
+        CU(ev_record(p, p->evb[0]));
+        CU(ev_record(p, p->pev[2][0]));
+        if ((rc = Pass<T>::x_part(p, eoff(p->work, (long long)(K - 1) * g.n0 * p->n1l * zk, p->esz), p->buf2, zk, K - 1, 0, A))) return rc;
+        CU(ev_record(p, p->pev[2][1]));
+        CU(ev_record(p, p->evb[1]));
+        if ((rc = flags_signal(p, 0, p->epoch, A))) return rc;
+        CU(ev_record(p, p->ev[2]));
+        CU(ev_record(p, p->ev[3]));
+        p->timed = true;
+        return 0;
+    }
     for (int k = 0; k < K; k++) {
         void* base[DFFT_MAX_CHUNKS];
         for (int q = 0; q < P; q++)
@@ -1821,6 +1885,8 @@ extern "C" int dfft_debug_timeline(dfft_plan p, double out[11])
     return 0;
 }
 extern "C" int dfft_plan_pipeline_parts(dfft_plan p) { return p && p->pipe ? p->parts : 0; }
+/* 1: the parts run as a chain of two-role kernels on one stream (fft_fused_yx_kernel), 0: two streams / not pipelined */
+extern "C" int dfft_plan_pipeline_chain(dfft_plan p) { return p && p->pipe && p->pipe_fyx ? 1 : 0; }
 extern "C" int dfft_plan_fused(dfft_plan p) { return p && p->fuse && p->xmode != DFFT_EXCHANGE_STAGED ? (p->overlap ? 2 : 1) : 0; }
 extern "C" void* dfft_plan_stream(dfft_plan p) { return p ? (void*)p->stream : nullptr; }
 

@@ -33,6 +33,8 @@ enum FusedKind {
 };
 typedef cudaError_t (*FusedLaunchFn)(const void* args_a, const void* args_b, const FusedCtl* ctl, int sm_count, cudaStream_t stream);
 // forward t0..t3 of one device in one kernel (fft_fused3_kernel): Z, Y with peer stores, X behind per-part arrival flags
+// send side (Y pass of part k, peer stores) and receive side (X pass of part k-1) of the exchange in one kernel (fft_fused_yx_kernel)
+typedef cudaError_t (*FusedYxLaunchFn)(const void* args_y, const void* args_x, const YxCtl* ctl, int sm_count, cudaStream_t stream);
 typedef cudaError_t (*Fused3LaunchFn)(const void* args_z, const void* args_y, const void* args_x, const Fused3Ctl* ctl, int sm_count, cudaStream_t stream);
 
 struct SizeEntry {
@@ -46,6 +48,7 @@ struct SizeEntry {
     PassLaunchFn launch[PK_COUNT];
     int f_zC, f_zCp;      // lines per contiguous tile inside the fused kernels (same CTA size as the strided role; p: peer-store kind)
     FusedLaunchFn fused[FK_COUNT];   // valid for square planes (N1 == N2 == N): both roles come from this entry
+    FusedYxLaunchFn fused_yx;        // Y (peer-store configuration) + X roles of this entry in one kernel; nullptr unless both fill the same CTA
     Fused3LaunchFn fused3;           // same restriction, and the X configuration must fill the same CTA as the peer-store Y role (else nullptr)
     const void* gen;      // run-time schedule (GenSched) of a generic-length entry, nullptr for tuned lengths
 };

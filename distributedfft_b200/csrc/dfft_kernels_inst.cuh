@@ -57,11 +57,41 @@ cudaError_t launch_fused(const void* va, const void* vb, const FusedCtl* ctl, in
     }
     if (ctl->planes <= 0) return cudaSuccess;
     const long long total = ctl->planes * ((long long)ctl->GA + ctl->GB);
+    if (total >= (1ll << 31)) return cudaErrorInvalidConfiguration;   // the kernel decodes tickets in 32 bits
     long long grid = (long long)sm_count * occ;
     if (grid > total) grid = total;
     FusedCtl c = *ctl;
     if (c.lag <= 0) c.lag = (int)((grid + c.GA + c.GB - 1) / ((long long)c.GA + c.GB)) + 1;   // role A stays one in-flight window ahead
     kern<<<(unsigned)grid, OpA::NT, smem, st>>>(a, b, c);
+    return cudaGetLastError();
+}
+
+template <class OpA, class OpB, typename T, int MINB>
+cudaError_t launch_fused_yx(const void* va, const void* vb, const YxCtl* ctl, int sm_count, cudaStream_t st)
+{
+    const TileArgs<T>& a = *reinterpret_cast<const TileArgs<T>*>(va);
+    const TileArgs<T>& b = *reinterpret_cast<const TileArgs<T>*>(vb);
+    auto kern = fft_fused_yx_kernel<OpA, OpB, T, MINB>;
+    constexpr size_t exch = OpA::SM::exch_bytes > OpB::SM::exch_bytes ? OpA::SM::exch_bytes : OpB::SM::exch_bytes;
+    constexpr size_t smem = exch + OpA::aux_bytes + OpB::aux_bytes;
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int occ = occ_cache[dev & 63].load();
+    if (occ == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OpA::NT, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        occ_cache[dev & 63].store(occ);
+    }
+    const long long total = (long long)ctl->TA + ctl->TB;
+    if (total <= 0) return cudaSuccess;
+    long long grid = (long long)sm_count * occ;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, OpA::NT, smem, st>>>(a, b, *ctl);
     return cudaGetLastError();
 }
 
@@ -90,6 +120,7 @@ cudaError_t launch_fused3(const void* va, const void* vb, const void* vc, const 
     }
     if (ctl->planes <= 0) return cudaSuccess;
     const long long total = ctl->planes * ((long long)ctl->GA + ctl->GB) + ctl->rows * (long long)ctl->GX;
+    if (total >= (1ll << 31)) return cudaErrorInvalidConfiguration;   // the kernel decodes tickets in 32 bits
     long long grid = (long long)sm_count * occ;
     if (grid > total) grid = total;
     Fused3Ctl f = *ctl;
@@ -167,7 +198,8 @@ SizeEntry make_entry(int variant = 0)
     if constexpr (XS::T * X::C == NTP) {
         using OX = TileOp<XS, T, X::C, MAP_C, MAP_T, false, false, false, false>;
         e.fused3 = launch_fused3<OZp, OYco, OX, T, (PEER::MB < X::MB ? PEER::MB : X::MB)>;
-    } else e.fused3 = nullptr;
+        e.fused_yx = launch_fused_yx<OYco, OX, T, (PEER::MB < X::MB ? PEER::MB : X::MB)>;
+    } else { e.fused3 = nullptr; e.fused_yx = nullptr; }
     return e;
 }
 

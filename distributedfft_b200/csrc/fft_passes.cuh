@@ -432,26 +432,28 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
     OpA::load_twiddles(ka, twa);
     OpB::load_twiddles(kb, twb);
 
-    const long long lag = F.lag < F.planes ? F.lag : F.planes;
-    const long long headT = lag * F.GA;                          // role A on planes [0, lag)
-    const long long midT = (F.planes - lag) * (F.GA + F.GB);     // pairs: A on plane lag+i, then B on plane i
-    const long long total = headT + midT + lag * F.GB;           // tail: B on the last `lag` planes
+    // ticket arithmetic in 32 bits (a ticket is decoded for every tile; 64-bit divisions cost several hundred cycles each)
+    const unsigned GA = (unsigned)F.GA, GB = (unsigned)F.GB, per = GA + GB;
+    const unsigned lag = (unsigned)(F.lag < F.planes ? F.lag : F.planes);
+    const unsigned headT = lag * GA;                                   // role A on planes [0, lag)
+    const unsigned midT = ((unsigned)F.planes - lag) * per;           // pairs: A on plane lag+i, then B on plane i
+    const unsigned total = headT + midT + lag * GB;                    // tail: B on the last `lag` planes
     for (;;) {
         __syncthreads();   // previous tile's smem traffic and s_ticket readers are done
         if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(F.ticket, 1u);
         __syncthreads();
-        const long long t = s_ticket;
+        const unsigned t = (unsigned)s_ticket;
         if (t >= total) break;
         bool roleA;
-        long long plane, idx;
-        if (t < headT) { roleA = true; plane = t / F.GA; idx = t - plane * F.GA; }
+        unsigned plane, idx;
+        if (t < headT) { roleA = true; plane = t / GA; idx = t - plane * GA; }
         else if (t < headT + midT) {
-            const long long u = t - headT, i = u / (F.GA + F.GB), r = u - i * (F.GA + F.GB);
-            if (r < F.GA) { roleA = true; plane = lag + i; idx = r; }
-            else { roleA = false; plane = i; idx = r - F.GA; }
+            const unsigned u = t - headT, i = u / per, r = u - i * per;
+            if (r < GA) { roleA = true; plane = lag + i; idx = r; }
+            else { roleA = false; plane = i; idx = r - GA; }
         } else {
-            const long long u = t - headT - midT, i = u / F.GB;
-            roleA = false; plane = F.planes - lag + i; idx = u - i * F.GB;
+            const unsigned u = t - headT - midT, i = u / GB;
+            roleA = false; plane = (unsigned)F.planes - lag + i; idx = u - i * GB;
         }
         if (roleA) {
             OpA::run(A, ka, (long long)plane * F.GA + idx, twa);
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
                 }
             }
             __syncthreads();
-            OpB::run(B, kb, plane * F.GB + idx, twb);
+            OpB::run(B, kb, (long long)plane * F.GB + idx, twb);
         }
     }
     if (B.sig_n > 0) __syncthreads();   // this CTA's (peer) stores happen-before thread 0's cumulative system-scope fence
@@ -485,6 +487,114 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
                 __threadfence_system();
                 for (int q = 0; q < B.sig_n; q++)
                     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(B.sig[q]), "l"(B.sig_val) : "memory");
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Send side and receive side of the exchange in ONE persistent kernel (forward, P2P): role A = the Y pass of z-part k
+// (its chunked stores land in the peers' receive buffers over NVLink), role B = the X pass of z-part k-1, which has
+// already arrived.  Both roles share every SM slot, so the NVLink-bound stores of A and the HBM-bound work of B overlap
+// without needing two co-resident kernels (two separate kernels each want both CTA slots of an SM: measured, they
+// serialise or halve each other).  Tickets: the first quarter of the A tiles, then blocks of 8 tickets (bx B tiles, 8 - bx
+// A tiles), then what is left of A, then of B.  A B tile only needs the arrival flags of its part (polled once per CTA);
+// nothing waits on another CTA of this kernel, so any residency is deadlock free.  The last CTA to leave publishes the
+// arrival flags of part k (A.sig) after every CTA's stores.
+// ------------------------------------------------------------------------------------------
+struct YxCtl {
+    unsigned int* ticket;                   // [0] next ticket, [1] CTAs that have left
+    const unsigned long long* my_arrive;    // arrival flags (per sender) of the part role B consumes
+    unsigned long long epoch;               // value those flags must have reached
+    int P;
+    unsigned TA, TB;                        // tiles of role A / role B
+};
+struct YxOrder { unsigned dly, bx, nblk, mixT, total; };
+__host__ __device__ inline YxOrder yx_prepare(const YxCtl& F)
+{
+    YxOrder o{};
+    o.dly = F.TA / 4;
+    const unsigned am = F.TA - o.dly;
+    unsigned bx = am + F.TB ? (unsigned)((8ull * F.TB + (am + F.TB) / 2) / (am + F.TB)) : 4;
+    bx = bx < 1 ? 1 : (bx > 7 ? 7 : bx);
+    o.bx = bx;
+    const unsigned nb = F.TB / bx, na = am / (8 - bx);
+    o.nblk = nb < na ? nb : na;
+    o.mixT = o.nblk * 8u;
+    o.total = F.TA + F.TB;
+    return o;
+}
+// ticket -> (is role B, tile index within the role)
+__host__ __device__ inline void yx_decode(const YxCtl& F, const YxOrder& o, unsigned t, bool& roleB, unsigned& idx)
+{
+    roleB = false;
+    if (t < o.dly) { idx = t; return; }
+    const unsigned v = t - o.dly;
+    if (v < o.mixT) {
+        const unsigned q = v >> 3, r = v & 7u;
+        if (r < o.bx) { roleB = true; idx = q * o.bx + r; }
+        else idx = o.dly + q * (8 - o.bx) + (r - o.bx);
+        return;
+    }
+    const unsigned w = v - o.mixT, rema = F.TA - o.dly - o.nblk * (8 - o.bx);
+    if (w < rema) idx = o.dly + o.nblk * (8 - o.bx) + w;
+    else { roleB = true; idx = o.nblk * o.bx + (w - rema); }
+}
+
+template <class OpA, class OpB, typename T, int MINB>
+__global__ void __launch_bounds__(OpA::NT, MINB) fft_fused_yx_kernel(const TileArgs<T> A, const TileArgs<T> B, const YxCtl F)
+{
+    static_assert(OpA::NT == OpB::NT, "both roles use the whole CTA");
+    constexpr size_t exch = OpA::SM::exch_bytes > OpB::SM::exch_bytes ? OpA::SM::exch_bytes : OpB::SM::exch_bytes;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_ticket;
+    typename OpA::Ctx ka;
+    typename OpB::Ctx kb;
+    OpA::setup(A, smem_raw, smem_raw + exch, ka);
+    OpB::setup(B, smem_raw, smem_raw + exch + OpA::aux_bytes, kb);
+    cx<T> twa[OpA::NTW], twb[OpB::NTW];
+    OpA::load_twiddles(ka, twa);
+    OpB::load_twiddles(kb, twb);
+    const YxOrder ord = yx_prepare(F);
+    bool arrived = false;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(F.ticket, 1u);
+        __syncthreads();
+        const unsigned t = s_ticket;
+        if (t >= ord.total) break;
+        bool roleB;
+        unsigned idx;
+        yx_decode(F, ord, t, roleB, idx);
+        if (!roleB) OpA::run(A, ka, (long long)idx, twa);
+        else {
+            if (!arrived) {   // the acquire loads of threads 0..P-1 order the senders' stores before everything after the bar.sync
+                if (threadIdx.x < F.P) {
+                    unsigned long long v;
+                    SpinGuard guard;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(F.my_arrive + threadIdx.x) : "memory");
+                        if (v >= F.epoch) break;
+                        __nanosleep(128);
+                        guard.tick();
+                    }
+                }
+                arrived = true;
+                __syncthreads();
+            }
+            OpB::run(B, kb, (long long)idx, twb);
+        }
+    }
+    if (A.sig_n > 0) __syncthreads();   // this CTA's peer stores happen-before thread 0's cumulative system-scope fence
+    if (threadIdx.x == 0) {
+        if (A.sig_n > 0) __threadfence_system();
+        const unsigned left = atomicAdd(F.ticket + 1, 1u);
+        if (left == gridDim.x - 1) {
+            F.ticket[0] = 0; F.ticket[1] = 0; __threadfence();
+            if (A.sig_n > 0) {
+                __threadfence_system();
+                for (int q = 0; q < A.sig_n; q++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.sig[q]), "l"(A.sig_val) : "memory");
             }
         }
     }

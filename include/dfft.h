@@ -188,6 +188,9 @@ int dfft_plan_tma_mask(dfft_plan plan);
 int dfft_debug_timeline(dfft_plan plan, double out[11]);
 /* number of z-parts of the stream-pipelined forward / backward path, 0 when the plan does not use it */
 int dfft_plan_pipeline_parts(dfft_plan plan);
+/* 1: the z-parts of a pipelined forward plan run as a chain of two-role kernels on one stream (Y pass of part k + X pass of
+ * part k-1 in one kernel: cubes with the P2P exchange), 0: as two streams, or not pipelined */
+int dfft_plan_pipeline_chain(dfft_plan plan);
 /* which exchange the plan resolved to (DFFT_EXCHANGE_*) */
 int dfft_plan_exchange(dfft_plan plan);
 /* the stream the plan launches on (a cudaStream_t), so callers can time with events on it */

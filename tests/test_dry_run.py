@@ -188,7 +188,7 @@ def test_single_kernel_forward_schedule(co, P, n):
         assert np.abs(got[d][: g.out_count(d)] - ref[d][: g.out_count(d)]).max() <= 1e-11 * scale
 
 
-PIPE_SHAPES = [("p2p", 2, 8, 128, 128, None), ("p2p", 4, 8, 12, 128, None), ("p2p", 3, 10, 9, 128, None), ("p2p", 8, 16, 64, 64, "2"),
+PIPE_SHAPES = [("p2p", 4, 64, 64, 64, "2"), ("p2p", 8, 64, 64, 64, "4"), ("p2p", 2, 8, 128, 128, None), ("p2p", 4, 8, 12, 128, None), ("p2p", 3, 10, 9, 128, None), ("p2p", 8, 16, 64, 64, "2"),
                ("p2p", 2, 6, 64, 64, "1"), ("nccl", 2, 8, 16, 128, None), ("nccl", 4, 8, 8, 64, "2"), ("nccl", 8, 64, 64, 64, "4")]
 
 
@@ -206,6 +206,9 @@ def test_stream_pipelined_forward_schedule(co, monkeypatch, mode, P, n0, n1, n2,
     flags = (dfft.EXCHANGE_P2P if mode == "p2p" else dfft.EXCHANGE_NCCL) | dfft.FORCE_PIPELINE
     got, names, fused = simulate(n0, n1, n2, P, FORWARD, inputs, flags)
     K = int(parts) if parts else 4
+    if mode == "p2p" and n0 == n1 == n2:
+        # cubes: chain of two-role kernels on one stream ([Z + Y0] [Y1 + X0] ... [X K-1]), fft_fused_yx_kernel
+        assert names[0] == ["fusedZ", "fusedY"] + ["Y_CO", "XF"] * (K - 1) + ["XF"], names[0]
     for d in range(P):
         assert names[d].count("XF") == K, names[d]
         if mode == "nccl":

@@ -37,7 +37,7 @@ MODES = {"p2p": dfft.EXCHANGE_P2P, "nccl": dfft.EXCHANGE_NCCL, "staged": dfft.EX
          "p2p-pipe": dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE, "nccl-pipe": dfft.EXCHANGE_NCCL | dfft.FORCE_PIPELINE,
          "p2p-nopipe": dfft.EXCHANGE_P2P | dfft.NO_PIPELINE}
 # (P, n0, n1, n2): even and uneven (short last slab in x and/or y) splits
-CASES = [(2, 4, 1024, 1024), (2, 6, 768, 768), (2, 30, 21, 10), (2, 16, 16, 16), (2, 6, 9, 9), (4, 12, 10, 10), (2, 10, 9, 4), (2, 64, 48, 96), (4, 12, 10, 24), (4, 64, 64, 64), (8, 64, 64, 64), (8, 100, 125, 8),
+CASES = [(2, 128, 128, 128), (4, 128, 128, 128), (2, 4, 1024, 1024), (2, 6, 768, 768), (2, 30, 21, 10), (2, 16, 16, 16), (2, 6, 9, 9), (4, 12, 10, 10), (2, 10, 9, 4), (2, 64, 48, 96), (4, 12, 10, 24), (4, 64, 64, 64), (8, 64, 64, 64), (8, 100, 125, 8),
          (8, 24, 48, 16)]
 
 
