@@ -670,8 +670,8 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
         if (p->fuse && !dry) {
             CUP(cudaMalloc((void**)&p->plane_done, (size_t)p->n0l * sizeof(unsigned long long)));
             CUP(cudaMemset(p->plane_done, 0, (size_t)p->n0l * sizeof(unsigned long long)));
-            CUP(cudaMalloc((void**)&p->ticket, 2 * sizeof(unsigned int)));
-            CUP(cudaMemset(p->ticket, 0, 2 * sizeof(unsigned int)));
+            CUP(cudaMalloc((void**)&p->ticket, 4 * sizeof(unsigned int)));
+            CUP(cudaMemset(p->ticket, 0, 4 * sizeof(unsigned int)));
         }
     }
 
@@ -773,6 +773,10 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
             }
             CUP(cudaMalloc((void**)&p->sync, sizeof(SyncBlock)));
             CUP(cudaMemset(p->sync, 0, sizeof(SyncBlock)));
+            if (xmode == DFFT_EXCHANGE_P2P && !p->done_ctr && !getenv("DFFT_SIGNAL_KERNELS")) {
+                CUP(cudaMalloc((void**)&p->done_ctr, DFFT_MAX_PARTS * sizeof(unsigned int)));
+                CUP(cudaMemset(p->done_ctr, 0, DFFT_MAX_PARTS * sizeof(unsigned int)));
+            }
             std::vector<void*> ps;
             if ((rc = share_pointer(p, p->sync, ps)) != 0) return bail(rc);
             p->peer_sync.resize(P);
@@ -853,6 +857,27 @@ extern "C" int dfft_memcpy(void* dst, const void* src, size_t bytes, int kind)
 // ------------------------------------------------------------------------------------------------
 // pass launches
 // ------------------------------------------------------------------------------------------------
+// start gate / completion signal folded into a pass kernel (TileArgs::wait_flags, TileArgs::sig) instead of separate
+// one-CTA launches: `which` 0 = ready[], 1 = arrive[], 2 + k = part_arrive[k]
+struct Fold {
+    int wait_which = -1; unsigned long long wait_val = 0;
+    int sig_which = -1; unsigned long long sig_val = 0;
+    int ctr = 0;     // which done_ctr word counts the finished CTAs of this launch
+};
+template <typename T> static void apply_fold(dfft_plan p, TileArgs<T>& a, const Fold* f)
+{
+    if (!f || p->dry || !p->sync) return;
+    auto mine = [&](int w) -> const unsigned long long* { return w == 0 ? p->sync->ready : (w == 1 ? p->sync->arrive : p->sync->part_arrive[w - 2]); };
+    if (f->wait_which >= 0 && f->wait_val > 0) { a.wait_flags = mine(f->wait_which); a.wait_val = f->wait_val; a.wait_n = p->P; }
+    if (f->sig_which >= 0) {
+        a.sig_n = p->P; a.sig_val = f->sig_val; a.done_ctr = p->done_ctr + f->ctr;
+        for (int q = 0; q < p->P; q++) {
+            SyncBlock* sb = p->peer_sync[q];
+            a.sig[q] = f->sig_which == 0 ? &sb->ready[p->me] : (f->sig_which == 1 ? &sb->arrive[p->me] : &sb->part_arrive[f->sig_which - 2][p->me]);
+        }
+    }
+}
+
 template <typename T> struct Pass {
     static int launch(dfft_plan p, const SizeEntry* e, int kind, TileArgs<T>& a, int axis_override = -1, cudaStream_t st = nullptr)
     {
@@ -925,7 +950,7 @@ template <typename T> struct Pass {
     }
     // columns of length N1 (stride N2) of every local plane.  mode 0: src -> dst natural (in place when equal)
     // mode 1: chunked (packed / peer) store, mode 2: chunked (unpack) load
-    static int y_pass(dfft_plan p, const void* src, void* dst, int mode, void* const* chunk_base)
+    static int y_pass(dfft_plan p, const void* src, void* dst, int mode, void* const* chunk_base, const Fold* fold = nullptr)
     {
         const Geom& g = p->g;
         if (mode == 0 && p->ty && (p->ty->use & (1u << TMA_Y)) && !p->dry && g.n2 % p->ty->C == 0) {
@@ -945,11 +970,12 @@ template <typename T> struct Pass {
             ct.ediv = (int)g.yd(); ct.nchunks = p->P;
             for (int q = 0; q < p->P; q++) { ct.cptr[q] = chunk_base[q]; ct.SAq[q] = g.n1l(q) * g.n2; }
         }
+        apply_fold<T>(p, a, fold);
         return launch(p, p->ey, mode == 0 ? PK_Y : (mode == 1 ? PK_Y_CO : PK_Y_CI), a);
     }
     // t0 in one persistent kernel (square planes): forward Z (zsrc -> mid) then Y (mid -> ydst, or chunked);
     // backward Y (ysrc or chunked -> mid) then Z (mid -> mid).  ymode as in y_pass.
-    static int zy_fused(dfft_plan p, const void* src, void* mid, void* dst, int ymode, void* const* chunk_base, bool scale)
+    static int zy_fused(dfft_plan p, const void* src, void* mid, void* dst, int ymode, void* const* chunk_base, bool scale, const Fold* fold = nullptr)
     {
         const Geom& g = p->g;
         const SizeEntry* e = p->ez;
@@ -977,6 +1003,7 @@ template <typename T> struct Pass {
         c.target = ++p->fuse_epoch * (unsigned long long)c.GA;
         c.lag = p->lag;
         const int kind = fwd ? (ymode == 1 ? FK_ZY_CO : FK_ZY) : (ymode == 2 ? FK_YZ_CI : FK_YZ);
+        apply_fold<T>(p, fwd ? y : z, fold);   // fft_fused2_kernel gates on / signals through its second role's arguments
         if (p->dry) {
             z.gen = y.gen = nullptr;
             if (fwd) { record_op<T>(p, "fusedZ", 0, e->N, CZ, false, false, false, z); record_op<T>(p, "fusedY", 0, e->N, CY, false, ymode == 1, false, y); }
@@ -1060,7 +1087,8 @@ template <typename T> struct Pass {
         return launch(p, p->ex, PK_Y, a, 2);   // a strided-local kernel, timed as the X pass
     }
     // forward X: src = [x][y_l][z] -> dst = [y_l][z][x]
-    static int x_fwd(dfft_plan p, const void* src, void* dst)
+    static bool x_fwd_folds(dfft_plan p) { return !(p->tx && (p->tx->use & (1u << TMA_XF)) && !p->dry && p->g.n2 % p->tx->C == 0); }
+    static int x_fwd(dfft_plan p, const void* src, void* dst, const Fold* fold = nullptr)
     {
         const Geom& g = p->g;
         if (p->tx && (p->tx->use & (1u << TMA_XF)) && !p->dry && g.n2 % p->tx->C == 0) {
@@ -1076,6 +1104,7 @@ template <typename T> struct Pass {
         a.G = (int)cdiv(g.n2, C); a.W = (int)g.n2; a.ntiles = p->n1l * a.G;
         a.ia = Affine{g.n2, C, 1, p->n1l * g.n2};
         a.oa = Affine{g.n2 * g.n0, (long long)C * g.n0, g.n0, 1};
+        apply_fold<T>(p, a, fold);
         return launch(p, p->ex, PK_XF, a);
     }
     // ---- z-part variants (stream-pipelined forward): part k of K covers the columns z in [k*zk, (k+1)*zk) ----------
@@ -1151,8 +1180,6 @@ template <typename T> struct Pass {
         x_part_args(p, x, rpart_prev, dst, zk, k - 1);
         YxCtl c{};
         c.ticket = p->ticket;
-        c.my_arrive = p->dry ? nullptr : &p->sync->part_arrive[k - 1][0];
-        c.epoch = p->epoch; c.P = p->P;
         c.TA = (unsigned)y.ntiles; c.TB = (unsigned)x.ntiles;
         if (p->dry) {
             record_op<T>(p, "Y_CO", 0, e->N, e->p_C, false, true, false, y);
@@ -1255,7 +1282,7 @@ template <typename T> struct Pass {
         return 0;
     }
     // backward X: src = [y_l][z][x] -> dst = [x][y_l][z] (chunked by destination device when chunk_base)
-    static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base)
+    static int x_bwd(dfft_plan p, const void* src, void* dst, void* const* chunk_base, const Fold* fold = nullptr)
     {
         const Geom& g = p->g;
         if (!chunk_base && p->tx && (p->tx->use & (1u << TMA_XB)) && !p->dry && g.n2 % p->tx->C == 0) {
@@ -1275,6 +1302,7 @@ template <typename T> struct Pass {
             a.co.ediv = (int)g.xd(); a.co.nchunks = p->P;
             for (int q = 0; q < p->P; q++) { a.co.cptr[q] = chunk_base[q]; a.co.SAq[q] = g.n2; }
         }
+        if (chunk_base) apply_fold<T>(p, a, fold);
         return launch(p, p->ex, chunk_base ? PK_XB_CO : PK_XB, a);
     }
 };
@@ -1439,7 +1467,12 @@ template <typename T> static int fwd_pipelined(dfft_plan p)
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], ((long long)k * g.n0 + (long long)me * g.xd()) * g.n1l(q) * zk, p->esz);
             if (k == 0) rc = Pass<T>::zy_fused_part0(p, p->buf1, p->mid, zk, base);
-            else rc = Pass<T>::yx_fused(p, p->mid, zk, k, base, eoff(p->work, (long long)(k - 1) * g.n0 * p->n1l * zk, p->esz), p->buf2);
+            else {
+                // part k-1 must have arrived from every sender before the kernel whose X role consumes it starts: a one-CTA gate
+                // kernel, not a poll inside the full-grid kernel (which would hold every SM slot while it waits, see execute_fused)
+                if ((rc = flags_wait(p, 2 + k - 1, p->epoch, A))) return rc;
+                rc = Pass<T>::yx_fused(p, p->mid, zk, k, base, eoff(p->work, (long long)(k - 1) * g.n0 * p->n1l * zk, p->esz), p->buf2);
+            }
             if (rc) return rc;
             if (!p->done_ctr && (rc = flags_signal(p, 2 + k, p->epoch, A))) return rc;   // else the kernel's last CTA publishes the flags
         }
@@ -1611,20 +1644,28 @@ template <typename T> static int execute_fused(dfft_plan p)
                 p->timed = true;
                 return 0;
             }
+            // The completion SIGNALS ride inside the pass kernels (their last CTA publishes the flags: 4 launches per transform
+            // instead of 6, DFFT_SIGNAL_KERNELS=1 restores the separate launches).  The GATES stay one-CTA kernels on purpose: a
+            // full-grid kernel that spins on a peer's flag holds every SM slot, and with two plans in flight per device (bench.py's
+            // e2e leg) device A can then wait for a kernel of device B that cannot start because B's SMs are held by a kernel waiting for A.
+            const bool fold = p->done_ctr != nullptr && !p->dry;
+            Fold fy; fy.sig_which = 1; fy.sig_val = p->epoch; fy.ctr = 0;
+            Fold fx; fx.sig_which = 0; fx.sig_val = p->epoch; fx.ctr = 1;
+            const bool foldx = fold && Pass<T>::x_fwd_folds(p);
             if (p->fuse) {
                 if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;   // every receiver has consumed the previous epoch
-                if ((rc = Pass<T>::zy_fused(p, p->buf1, p->buf2, nullptr, 1, base, false))) return rc;
+                if ((rc = Pass<T>::zy_fused(p, p->buf1, p->buf2, nullptr, 1, base, false, fold ? &fy : nullptr))) return rc;
             } else {
                 if ((rc = Pass<T>::z_pass(p, p->buf1, p->buf2, false))) return rc;
                 if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;
-                if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base))) return rc;
+                if ((rc = Pass<T>::y_pass(p, p->buf2, nullptr, 1, base, fold ? &fy : nullptr))) return rc;
             }
-            if ((rc = flags_signal(p, 1, p->epoch))) return rc;
+            if (!fold && (rc = flags_signal(p, 1, p->epoch))) return rc;
             CU(ev_record(p, p->ev[1]));
             if ((rc = flags_wait(p, 1, p->epoch))) return rc;        // t2: exposed wait for the slowest sender
             CU(ev_record(p, p->ev[2]));
-            if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2))) return rc;
-            if ((rc = flags_signal(p, 0, p->epoch))) return rc;
+            if ((rc = Pass<T>::x_fwd(p, p->work, p->buf2, foldx ? &fx : nullptr))) return rc;
+            if (!foldx && (rc = flags_signal(p, 0, p->epoch))) return rc;
         } else {
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->buf2, send_off(g, me, q, DFFT_FORWARD), p->esz);
@@ -1651,19 +1692,23 @@ template <typename T> static int execute_fused(dfft_plan p)
             else if ((rc = Pass<T>::y_pass(p, p->buf2, p->buf2, 0, nullptr))) return rc;
         } else if (p->xmode == DFFT_EXCHANGE_P2P) {
             p->epoch++;
+            const bool fold = p->done_ctr != nullptr && !p->dry;
+            Fold fxb; fxb.sig_which = 1; fxb.sig_val = p->epoch; fxb.ctr = 0;      // signals folded, gates separate (see the forward branch)
+            Fold fyz; fyz.ctr = 1;
+            if (p->fuse) { fyz.sig_which = 0; fyz.sig_val = p->epoch; }   // the fused kernel is the last one: it also signals "consumed"
             if ((rc = flags_wait(p, 0, p->epoch - 1))) return rc;
             void* base[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) base[q] = eoff(p->peer_work[q], recv_off(g, me, q, DFFT_BACKWARD), p->esz);
-            if ((rc = Pass<T>::x_bwd(p, p->buf1, nullptr, base))) return rc;
-            if ((rc = flags_signal(p, 1, p->epoch))) return rc;
+            if ((rc = Pass<T>::x_bwd(p, p->buf1, nullptr, base, fold ? &fxb : nullptr))) return rc;
+            if (!fold && (rc = flags_signal(p, 1, p->epoch))) return rc;
             CU(ev_record(p, p->ev[1]));
             if ((rc = flags_wait(p, 1, p->epoch))) return rc;
             CU(ev_record(p, p->ev[2]));
             void* cb[DFFT_MAX_CHUNKS];
             for (int q = 0; q < P; q++) cb[q] = eoff(p->work, (long long)q * p->n0l * g.yd() * g.n2, p->esz);
-            if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale))) return rc; }
-            else if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb))) return rc;
-            if ((rc = flags_signal(p, 0, p->epoch))) return rc;
+            if (p->fuse) { if ((rc = Pass<T>::zy_fused(p, nullptr, p->buf2, nullptr, 2, cb, scale, fold ? &fyz : nullptr))) return rc; }
+            else if ((rc = Pass<T>::y_pass(p, nullptr, p->buf2, 2, cb, fold ? &fyz : nullptr))) return rc;
+            if (!(fold && p->fuse) && (rc = flags_signal(p, 0, p->epoch))) return rc;
         } else {
             if ((rc = Pass<T>::x_bwd(p, p->buf1, p->buf2, nullptr))) return rc;
             CU(ev_record(p, p->ev[1]));

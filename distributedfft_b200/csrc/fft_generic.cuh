@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fft_generic_kernel(const TileArgs
     const bool inv = A.inv != 0;
     const int total = C * N;
 
+    wait_flags_at_start<T>(A);
     for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const long long a = tile / A.G;
         const int b = (int)(tile - a * A.G);

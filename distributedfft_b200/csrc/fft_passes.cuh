@@ -51,6 +51,11 @@ template <typename T> struct TileArgs {
     unsigned long long sig_val;
     unsigned int* done_ctr;
     int sig_n;
+    // start gate folded into the kernel: when wait_n > 0 every CTA first polls wait_flags[0..wait_n) (system-scope acquire) until
+    // they reach wait_val -- "every sender's data has arrived" / "every receiver has consumed the previous execute"
+    const unsigned long long* wait_flags;
+    unsigned long long wait_val;
+    int wait_n;
     int max_ctas_per_sm;   // launcher only: cap on resident CTAs per SM (0 = occupancy limit); the stream-pipelined forward path
                            // leaves SM slots free so that the send-side Y parts and the receive-side X parts co-reside
 };
@@ -166,6 +171,24 @@ template <int H, typename C_> __device__ __forceinline__ void st_pol(C_* p, C_ v
 {
     if constexpr (H == 0) st_stream(p, v);
     else st_hint(p, v, pol);
+}
+
+// Called by every thread of a CTA before its first load (see TileArgs::wait_flags).
+template <typename T>
+__device__ __forceinline__ void wait_flags_at_start(const TileArgs<T>& A)
+{
+    if (A.wait_n <= 0) return;
+    if ((int)threadIdx.x < A.wait_n) {
+        unsigned long long v;
+        SpinGuard guard;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.wait_flags + threadIdx.x) : "memory");
+            if (v >= A.wait_val) break;
+            __nanosleep(100);
+            guard.tick();
+        }
+    }
+    __syncthreads();
 }
 
 // Called by every thread of a CTA after its last store.  Orders the CTA's (peer) stores at system scope, counts the CTA and --
@@ -388,6 +411,7 @@ __global__ void __launch_bounds__(S::T* C, MINB) fft_tile_kernel(const TileArgs<
     Op::setup(A, smem_raw, smem_raw + Op::SM::exch_bytes, k);
     cx<T> twr[Op::NTW];
     Op::load_twiddles(k, twr);
+    wait_flags_at_start<T>(A);
     if (PF && (long long)blockIdx.x < A.ntiles) Op::prefetch(A, k, blockIdx.x);
     for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const long long next = tile + gridDim.x;
@@ -431,6 +455,7 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
     cx<T> twa[OpA::NTW], twb[OpB::NTW];
     OpA::load_twiddles(ka, twa);
     OpB::load_twiddles(kb, twb);
+    wait_flags_at_start<T>(B);   // the second role's stores may target buffers a peer is still reading (previous execute)
 
     // ticket arithmetic in 32 bits (a ticket is decoded for every tile; 64-bit divisions cost several hundred cycles each)
     const unsigned GA = (unsigned)F.GA, GB = (unsigned)F.GB, per = GA + GB;
@@ -495,51 +520,20 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused2_kernel(const TileArg
 // ------------------------------------------------------------------------------------------
 // Send side and receive side of the exchange in ONE persistent kernel (forward, P2P): role A = the Y pass of z-part k
 // (its chunked stores land in the peers' receive buffers over NVLink), role B = the X pass of z-part k-1, which has
-// already arrived.  Both roles share every SM slot, so the NVLink-bound stores of A and the HBM-bound work of B overlap
-// without needing two co-resident kernels (two separate kernels each want both CTA slots of an SM: measured, they
-// serialise or halve each other).  Tickets: the first quarter of the A tiles, then blocks of 8 tickets (bx B tiles, 8 - bx
-// A tiles), then what is left of A, then of B.  A B tile only needs the arrival flags of its part (polled once per CTA);
-// nothing waits on another CTA of this kernel, so any residency is deadlock free.  The last CTA to leave publishes the
-// arrival flags of part k (A.sig) after every CTA's stores.
+// already arrived (a one-CTA gate kernel in front of this launch has seen the flags).
+// Two separate kernels cannot overlap here -- each wants both CTA slots of every SM, so they serialise or halve each other
+// (measured) -- and handing out A and B tiles from ONE ordered ticket stream does not overlap either: a CTA stalled on
+// back-pressured NVLink stores keeps its slot, the short B tiles finish, their CTAs draw the next ticket, and soon every slot
+// holds a stalled A tile (measured: the B work simply added to the send time).  So the roles are PINNED: the first half of the
+// grid (one CTA per SM) prefers A tiles, the second half prefers B tiles, each with its own ticket counter; a CTA only
+// crosses over when its own kind is exhausted.  Every SM then always has one slot feeding NVLink and one slot doing the
+// HBM-bound X work.  Nothing in this kernel waits on another CTA or another device, so any residency is deadlock free.
+// The last CTA to leave publishes the arrival flags of part k (A.sig) after every CTA's stores.
 // ------------------------------------------------------------------------------------------
 struct YxCtl {
-    unsigned int* ticket;                   // [0] next ticket, [1] CTAs that have left
-    const unsigned long long* my_arrive;    // arrival flags (per sender) of the part role B consumes
-    unsigned long long epoch;               // value those flags must have reached
-    int P;
+    unsigned int* ticket;                   // [0] next A tile, [1] CTAs that have left, [2] next B tile
     unsigned TA, TB;                        // tiles of role A / role B
 };
-struct YxOrder { unsigned dly, bx, nblk, mixT, total; };
-__host__ __device__ inline YxOrder yx_prepare(const YxCtl& F)
-{
-    YxOrder o{};
-    o.dly = F.TA / 4;
-    const unsigned am = F.TA - o.dly;
-    unsigned bx = am + F.TB ? (unsigned)((8ull * F.TB + (am + F.TB) / 2) / (am + F.TB)) : 4;
-    bx = bx < 1 ? 1 : (bx > 7 ? 7 : bx);
-    o.bx = bx;
-    const unsigned nb = F.TB / bx, na = am / (8 - bx);
-    o.nblk = nb < na ? nb : na;
-    o.mixT = o.nblk * 8u;
-    o.total = F.TA + F.TB;
-    return o;
-}
-// ticket -> (is role B, tile index within the role)
-__host__ __device__ inline void yx_decode(const YxCtl& F, const YxOrder& o, unsigned t, bool& roleB, unsigned& idx)
-{
-    roleB = false;
-    if (t < o.dly) { idx = t; return; }
-    const unsigned v = t - o.dly;
-    if (v < o.mixT) {
-        const unsigned q = v >> 3, r = v & 7u;
-        if (r < o.bx) { roleB = true; idx = q * o.bx + r; }
-        else idx = o.dly + q * (8 - o.bx) + (r - o.bx);
-        return;
-    }
-    const unsigned w = v - o.mixT, rema = F.TA - o.dly - o.nblk * (8 - o.bx);
-    if (w < rema) idx = o.dly + o.nblk * (8 - o.bx) + w;
-    else { roleB = true; idx = o.nblk * o.bx + (w - rema); }
-}
 
 template <class OpA, class OpB, typename T, int MINB>
 __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused_yx_kernel(const TileArgs<T> A, const TileArgs<T> B, const YxCtl F)
@@ -547,7 +541,8 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused_yx_kernel(const TileA
     static_assert(OpA::NT == OpB::NT, "both roles use the whole CTA");
     constexpr size_t exch = OpA::SM::exch_bytes > OpB::SM::exch_bytes ? OpA::SM::exch_bytes : OpB::SM::exch_bytes;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned s_ticket;
+    __shared__ int s_role;
+    __shared__ unsigned s_idx;
     typename OpA::Ctx ka;
     typename OpB::Ctx kb;
     OpA::setup(A, smem_raw, smem_raw + exch, ka);
@@ -555,42 +550,37 @@ __global__ void __launch_bounds__(OpA::NT, MINB) fft_fused_yx_kernel(const TileA
     cx<T> twa[OpA::NTW], twb[OpB::NTW];
     OpA::load_twiddles(ka, twa);
     OpB::load_twiddles(kb, twb);
-    const YxOrder ord = yx_prepare(F);
-    bool arrived = false;
+    const bool prefer_b = blockIdx.x >= (gridDim.x + 1) / 2;
+    bool a_left = F.TA > 0, b_left = F.TB > 0;   // thread 0's view: tiles of that kind may still be unclaimed
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(F.ticket, 1u);
-        __syncthreads();
-        const unsigned t = s_ticket;
-        if (t >= ord.total) break;
-        bool roleB;
-        unsigned idx;
-        yx_decode(F, ord, t, roleB, idx);
-        if (!roleB) OpA::run(A, ka, (long long)idx, twa);
-        else {
-            if (!arrived) {   // the acquire loads of threads 0..P-1 order the senders' stores before everything after the bar.sync
-                if (threadIdx.x < F.P) {
-                    unsigned long long v;
-                    SpinGuard guard;
-                    for (;;) {
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(F.my_arrive + threadIdx.x) : "memory");
-                        if (v >= F.epoch) break;
-                        __nanosleep(128);
-                        guard.tick();
-                    }
+        if (threadIdx.x == 0) {
+            int role = -1;
+            unsigned idx = 0;
+#pragma unroll
+            for (int attempt = 0; attempt < 2; attempt++) {
+                const bool try_b = (attempt == 0) == prefer_b;
+                if (role < 0 && (try_b ? b_left : a_left)) {
+                    const unsigned t = atomicAdd(F.ticket + (try_b ? 2 : 0), 1u);
+                    if (t < (try_b ? F.TB : F.TA)) { role = try_b ? 1 : 0; idx = t; }
+                    else if (try_b) b_left = false;
+                    else a_left = false;
                 }
-                arrived = true;
-                __syncthreads();
             }
-            OpB::run(B, kb, (long long)idx, twb);
+            s_role = role; s_idx = idx;
         }
+        __syncthreads();
+        const int role = s_role;
+        if (role < 0) break;
+        if (role == 0) OpA::run(A, ka, (long long)s_idx, twa);
+        else OpB::run(B, kb, (long long)s_idx, twb);
     }
     if (A.sig_n > 0) __syncthreads();   // this CTA's peer stores happen-before thread 0's cumulative system-scope fence
     if (threadIdx.x == 0) {
         if (A.sig_n > 0) __threadfence_system();
         const unsigned left = atomicAdd(F.ticket + 1, 1u);
         if (left == gridDim.x - 1) {
-            F.ticket[0] = 0; F.ticket[1] = 0; __threadfence();
+            F.ticket[0] = 0; F.ticket[1] = 0; F.ticket[2] = 0; __threadfence();
             if (A.sig_n > 0) {
                 __threadfence_system();
                 for (int q = 0; q < A.sig_n; q++)
