@@ -382,7 +382,8 @@ def run_dfft_arm(args):
         # the forward transform of a device is a two-stream pipeline of part kernels (send side: Z, Y parts with the pack and the
         # peer stores / ncclAlltoAll; receive side: X parts): no single kernel dominates, the roofline is quoted on the whole
         # transform with SURVEY 8(d)'s algorithmic bytes (6 + 2) * E * M per GPU
-        kernels = [("whole forward transform, stream-pipelined over %d z-parts (send side: Z + Y/pack/exchange parts; receive side: X parts)" % plan.pipeline_parts,
+        kernels = [(("whole forward transform, chain of two-role kernels over %d z-parts ([Z + Y0] [Y1 + X0] ... [X last]; fft_fused2_kernel, fft_fused_yx_kernel)" if plan.pipeline_chain else
+                     "whole forward transform, stream-pipelined over %d z-parts (send side: Z + Y/pack/exchange parts; receive side: X parts)") % plan.pipeline_parts,
                     ms_per_step, 4 * slab_bytes, 4 * slab_bytes, "fwd_pipelined")]
     elif plan.overlapped:
         # the whole forward transform of a device is ONE kernel (Z, Y with peer stores, X behind arrival flags): compulsory
@@ -416,7 +417,8 @@ def run_dfft_arm(args):
         "config": {"workload": f"{n}x{n}x{n} C2C {args.precision} forward, slab decomposition over {P} GPU(s)",
                    "exchange": {1: "p2p-fused", 2: "nccl", 3: "staged"}[plan.exchange] if P > 1 else "none",
                    "l2": "inputs (%.2f GiB per GPU) exceed the 126 MB L2; no flush needed" % (M * esz / 2 ** 30),
-                   "parallelism": f"slab{P}", "pipeline_parts": plan.pipeline_parts, "t0": "overlapped-single-kernel" if plan.overlapped else ("fused-L2" if plan.fused else "two-sweep")},
+                   "parallelism": f"slab{P}", "pipeline_parts": plan.pipeline_parts,
+                   "pipeline": ("kernel-chain" if plan.pipeline_chain else "two-stream") if plan.pipeline_parts else "none", "t0": "overlapped-single-kernel" if plan.overlapped else ("fused-L2" if plan.fused else "two-sweep")},
         "stage_ms": {"t0": stage[0], "t1": stage[1], "t2": stage[2], "t3": stage[3], "total": stage[4]},
         "pass_ms": ({"send_side_z_y_parts": passes_avg[0], "receive_side_x_parts_span": passes_avg[2]} if plan.pipeline_parts else
                     {"forward_single_kernel": passes_avg[0]} if plan.overlapped else {"t0_fused_zy": passes_avg[0], "x": passes_avg[2]} if plan.fused else

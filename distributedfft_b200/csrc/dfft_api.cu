@@ -707,13 +707,20 @@ static int plan_create(long long n0, long long n1, long long n2, void* in, void*
     {
         // stream-pipelined forward (z-parts): send side and receive side on two streams, see fwd_pipelined
         const char* env = getenv("DFFT_PIPELINE");
-        // Policy (profiles/r2_sweep_pipeline_*gpu.log): with 2 devices the transform is HBM-bound and already at ~95 % of its
-        // (6+2) E M roofline without any overlap, so cutting it into parts only adds launches and a second read of the
-        // intermediate (512^3: 1.38 ms plain, 1.43 / 1.53 ms with 2 / 4 parts); from 4 devices on the exchange is NVLink-bound
-        // and the receive-side X pass is what the pipeline hides.  NCCL collectives compete with the part kernels for SMs
-        // (2.47 ms plain vs 2.8-3.0 ms pipelined at 2 devices): opt-in there.  DFFT_FORCE_PIPELINE / DFFT_PIPELINE=1 override.
+        // Policy, from the sweeps under profiles/ (r2_sweep_pipeline_{2,4}gpu.log, r2_sweep_kernel_chain*_{2,4}gpu.log):
+        //  * 2 devices: the transform is HBM / L2-fabric bound and already at ~95 % of its (6+2) E M roofline without overlap
+        //    (512^3: 1.38 ms plain, 1.43-1.57 ms in parts): never pipelined by default.
+        //  * two streams (any exchange): a Y-part kernel and an X-part kernel each want both CTA slots of an SM, so they
+        //    serialise or halve each other; NCCL's kernels compete for the same slots (4 devices, 512^3: 0.86 ms plain, 0.97-1.10 ms
+        //    two-stream, NCCL 1.47 vs 1.50-1.62): opt-in only.
+        //  * kernel chain (cubes, P2P): [Z + Y0] [Y1 + X0] ... [X last] with the two roles pinned to the two CTA slots of every SM.
+        //    4 devices: 1024^3 8.79 -> 7.47 ms (-15 %), 512^3 0.87 -> 0.86 ms (a tie), 768^3 fp32 and 256^3 slightly slower.
+        //    Default from 4 devices on for axes >= 1024 points, where the X pass that it hides is long enough to pay for the
+        //    extra launches and the second read of the intermediate.
+        // DFFT_FORCE_PIPELINE / DFFT_PIPELINE=1 pipeline wherever it is possible, DFFT_NO_PIPELINE / DFFT_PIPELINE=0 never.
         const bool possible = P > 1 && !p->overlap && (xmode == DFFT_EXCHANGE_P2P || xmode == DFFT_EXCHANGE_NCCL);
-        bool want = possible && xmode == DFFT_EXCHANGE_P2P && P >= 4;
+        const bool chain_ok = direction == DFFT_FORWARD && xmode == DFFT_EXCHANGE_P2P && p->fuse && ey == ex && ey->fused_yx != nullptr;
+        bool want = possible && chain_ok && P >= 4 && n2 >= 1024;
         if (env) want = possible && strcmp(env, "0") != 0;
         if (flags & DFFT_FORCE_PIPELINE) want = possible;
         if (direction == DFFT_BACKWARD && getenv("DFFT_PIPELINE_BWD") && !strcmp(getenv("DFFT_PIPELINE_BWD"), "0")) want = false;

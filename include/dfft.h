@@ -60,13 +60,14 @@ extern "C" {
                                     the z axis is sent in parts and the X lines of a part start as soon as it has arrived
                                     from every sender, overlapping t3 with the NVLink-bound sends (env DFFT_OVERLAP=1) */
 
-#define DFFT_NO_PIPELINE 256u     /* P > 1: do NOT cut the z axis into parts.  Stream-pipelined plans run the send side (Z, then per
-                                    part the Y pass + pack + peer stores / ncclAlltoAll; backward: inverse X parts) and the receive
-                                    side (X pass of a part once it has arrived from every sender; backward: inverse Y parts, inverse
-                                    Z) on two streams, so t2 and t3 overlap t0 -- the reference has no overlap at all
-                                    (fft_mpi_3d_api.cpp:610-672).  Default: P2P exchange with >= 4 devices.
-                                    env DFFT_PIPELINE=0 / 1 overrides, DFFT_PARTS=k picks the number of parts */
-#define DFFT_FORCE_PIPELINE 1024u /* stream-pipelined plan wherever it is possible (2 devices, NCCL exchange with equal chunks) */
+#define DFFT_NO_PIPELINE 256u     /* P > 1: do NOT cut the z axis into parts.  Pipelined plans overlap t2 / t3 with t0 -- the reference has no
+                                    overlap at all (fft_mpi_3d_api.cpp:610-672).  Two schedules exist: a CHAIN of two-role kernels on
+                                    the plan stream, [Z + Y part 0] [Y part 1 + X part 0] ... [X last part] (forward, cubes, P2P
+                                    exchange), and a TWO-STREAM schedule (send side / receive side, any direction, P2P or NCCL).
+                                    Default (measured): the chain, from 4 devices on, for axes >= 1024 points.
+                                    env DFFT_PIPELINE=0 / 1 overrides, DFFT_PARTS=k picks the number of parts,
+                                    DFFT_PIPE_MODE=streams prefers the two-stream schedule */
+#define DFFT_FORCE_PIPELINE 1024u /* pipelined plan wherever one is possible (also 2 devices, short axes, backward, NCCL with equal chunks) */
 
 #define DFFT_NO_TMA 512u          /* use the register-staged pass kernels everywhere.  Default: passes whose load and store are both
                                     local and un-chunked (Z, natural Y, X) run on the TMA-pipelined kernels (fft_tma.cuh: 3-slot
