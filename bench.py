@@ -385,6 +385,11 @@ def run_dfft_arm(args):
         kernels = [(("whole forward transform, chain of two-role kernels over %d z-parts ([Z + Y0] [Y1 + X0] ... [X last]; fft_fused2_kernel, fft_fused_yx_kernel)" if plan.pipeline_chain else
                      "whole forward transform, stream-pipelined over %d z-parts (send side: Z + Y/pack/exchange parts; receive side: X parts)") % plan.pipeline_parts,
                     ms_per_step, 4 * slab_bytes, 4 * slab_bytes, "fwd_pipelined")]
+    elif P > 1 and not plan.overlapped:
+        # multi-GPU, plain schedule: t0 (Z + Y + NVLink peer stores in one kernel) is NVLink-bound, not HBM-bound, so a per-kernel
+        # HBM fraction would mislead; SURVEY 8(d) defines the multi-GPU roofline on the whole transform: (6 + 2) * E * M / t_forward
+        kernels = [("whole forward transform (fused Z+Y with NVLink peer stores, gate, X pass); t0 %.3f ms, X %.3f ms" % (passes_avg[0], passes_avg[2]),
+                    ms_per_step, 4 * slab_bytes, 4 * slab_bytes, "fwd_multi")]
     elif plan.overlapped:
         # the whole forward transform of a device is ONE kernel (Z, Y with peer stores, X behind arrival flags): compulsory
         # HBM traffic = slab read + intermediate write-back + receive-buffer read + result write = 4*E*M
