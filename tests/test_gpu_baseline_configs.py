@@ -17,12 +17,14 @@ import distributedfft_b200 as dfft  # noqa: E402
 from oracle import BACKWARD, FORWARD, COracle, NumpySlab, SlabGeometry  # noqa: E402
 from gpu_helpers import run_slab  # noqa: E402
 
-CONFIGS = [("C2", 512, 1, dfft.DOUBLE), ("C3", 512, 4, dfft.DOUBLE), ("C3b", 512, 8, dfft.DOUBLE), ("C3c", 512, 2, dfft.DOUBLE),
-           ("C4", 1024, 8, dfft.DOUBLE), ("C5", 768, 8, dfft.FLOAT)]
+CONFIGS = [("C2", 512, 1, dfft.DOUBLE, 0), ("C3", 512, 4, dfft.DOUBLE, 0), ("C3b", 512, 8, dfft.DOUBLE, 0), ("C3c", 512, 2, dfft.DOUBLE, 0),
+           # the pipelined schedules at full size, also where they are not the default (kernel chain for the cube)
+           ("C3-chain", 512, 4, dfft.DOUBLE, dfft.FORCE_PIPELINE), ("C3c-chain", 512, 2, dfft.DOUBLE, dfft.FORCE_PIPELINE),
+           ("C4", 1024, 8, dfft.DOUBLE, 0), ("C5", 768, 8, dfft.FLOAT, 0)]
 
 
-@pytest.mark.parametrize("name,n,P,precision", CONFIGS, ids=[c[0] for c in CONFIGS])
-def test_full_size_forward_spectrum_and_round_trip_vs_oracle(name, n, P, precision):
+@pytest.mark.parametrize("name,n,P,precision,flags", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_full_size_forward_spectrum_and_round_trip_vs_oracle(name, n, P, precision, flags):
     if torch.cuda.device_count() < P:
         pytest.skip(f"needs {P} GPUs, box has {torch.cuda.device_count()}")
     co = COracle()
@@ -37,7 +39,7 @@ def test_full_size_forward_spectrum_and_round_trip_vs_oracle(name, n, P, precisi
     co.slab_execute(g, b1, b2, FORWARD)          # oracle: reference stages t0..t3 on P "devices"
     del b1
     cast = (lambda x: x) if precision == dfft.DOUBLE else (lambda x: x.astype(np.complex64))
-    res = run_slab(n, n, n, P, FORWARD, [cast(b) for b in inputs], precision=precision, repeat=2, refill=False)
+    res = run_slab(n, n, n, P, FORWARD, [cast(b) for b in inputs], precision=precision, repeat=2, refill=False, flags=flags)
     scale = max(np.abs(r[: g.out_count(q)]).max() for q, r in enumerate(b2))
     tol = 1e-12 * np.log2(float(n) ** 3) if precision == dfft.DOUBLE else 5e-6
     for q in range(P):
@@ -48,7 +50,7 @@ def test_full_size_forward_spectrum_and_round_trip_vs_oracle(name, n, P, precisi
         assert res[0]["exchange"] == dfft.EXCHANGE_P2P
     spectra = [r["buf2"] for r in res]
     del res, b2
-    back = run_slab(n, n, n, P, BACKWARD, spectra, precision=precision)
+    back = run_slab(n, n, n, P, BACKWARD, spectra, precision=precision, flags=flags)
     rt_tol = 1e-11 if precision == dfft.DOUBLE else 5e-4
     for p in range(P):
         cnt = g.in_count(p)
