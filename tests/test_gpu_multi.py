@@ -209,14 +209,11 @@ def test_process_per_gpu_bootstrap(tmp_path, mode):
         assert f"rank {k} ok" in r.stdout
 
 
-EXPERIMENTAL = os.environ.get("DFFT_TEST_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental overlapped forward kernel: set DFFT_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("P,n", [(2, 64), (4, 64), (8, 64), (2, 128), (2, 256), (8, 256)])
 def test_overlapped_forward_matches_default_path(P, n):
-    """DFFT_OVERLAP_X (fft_fused3_kernel: Z + Y/peer-store + X roles, per-part arrival flags) must produce the same
-    y-slabs as the default P2P path, bit for bit, over repeated executes."""
+    """DFFT_OVERLAP_X (fft_fused3_kernel: Z + Y/peer-store + X roles of all z-parts from one ticket stream, per-part arrival
+    flags published once per CTA and part) must produce the same y-slabs as the plain P2P path, bit for bit, over repeated
+    executes.  Validated on hardware in round 2 (slower than the plain path, DESIGN.md 5.1: kept as an experiment)."""
     need(P)
     n0 = n   # the single-kernel path needs a cube (all three axes share one table entry)
     ns = NumpySlab(n0, n, n, P)
