@@ -32,9 +32,15 @@ try:
     CPUS_ALLOWED = sorted(os.sched_getaffinity(0))
 except AttributeError:
     CPUS_ALLOWED = list(range(os.cpu_count() or 1))
-# CPU legs: threads bound to cores, one per place (must be set before the first OpenMP runtime starts)
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def pin_openmp_threads():
+    """CPU legs only: OpenMP threads bound to cores, one per place.  Must run before the OpenMP runtime in question starts (the
+    oracle's libgomp), and must NOT be set for the GPU arm's processes: under torchrun every rank's main thread would be bound to
+    the first place -- the same core -- and the ranks' kernel launches would time-share it (measured: 512^3 on 4 GPUs 1.88 ms per
+    step host-bound against 0.87 ms of device time, profiles/r2_final_bench_n4_hostbound.json)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 
 def flops(n0, n1, n2):
@@ -207,6 +213,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    pin_openmp_threads()
     n = args.size
     r = ref_forward_rate(n, args.steps, args.warmup, budget_s=150.0, precision=args.precision)
     arm = "the reference tree's own CPU FFT: heFFTe 2.1.0 stock backend (oracle/_ref, built from /root/reference/heffte/heffteBenchmark)"
@@ -442,6 +449,7 @@ def run_dfft_arm(args):
     if P == 1 and rank == 0 and not args.no_cpu:
         # reported baseline (not the target): the reference tree's heFFTe on the host cores, bounded to ~20 s; beside it the
         # OpenMP oracle port and scipy's pocketfft, a few seconds each
+        pin_openmp_threads()   # affects the oracle port's OpenMP runtime, which starts below; torch's runtime is already up
         r = ref_forward_rate(n, steps=5, warmup=1, budget_s=20.0, precision=args.precision)
         kind = "reference"
         if r is None:
