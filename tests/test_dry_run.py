@@ -336,3 +336,36 @@ def test_random_geometries_all_exchanges(co):
             n = g.out_count(d) if direction == FORWARD else g.in_count(d)
             assert np.abs(got[d][:n] - ref[d][:n]).max() <= 1e-11 * scale, (P, n0, n1, n2, flags, direction, d, names[d])
         done += 1
+
+
+def test_default_pipeline_policy(monkeypatch):
+    """Which schedule a plan picks by default (dfft_plan_c2c_3d, measured policy of DESIGN.md 5.1): the kernel chain for cubes
+    with axes >= 1024 points from 4 devices on (P2P), the plain schedule everywhere else; flags and environment override."""
+    for var in ("DFFT_PIPELINE", "DFFT_PARTS", "DFFT_PIPE_MODE"):
+        monkeypatch.delenv(var, raising=False)
+
+    def plan(n0, n1, n2, P, flags=0, direction=FORWARD):
+        p = dfft.fft_mpi_plan_dft_c2c_3d(n0, n1, n2, fake(0, IN), fake(0, OUT), None, 0, P, direction, dfft.DOUBLE, flags | dfft.DRY_RUN)
+        out = (p.pipeline_parts, p.pipeline_chain)
+        p.destroy()
+        return out
+
+    assert plan(1024, 1024, 1024, 4) == (4, True)
+    assert plan(1024, 1024, 1024, 8) == (4, True)
+    assert plan(1024, 1024, 1024, 2) == (0, False)                         # 2 devices: L2-fabric bound, nothing to hide
+    assert plan(512, 512, 512, 8) == (0, False)                            # short X pass: a tie at 4 devices, not the default
+    assert plan(768, 768, 768, 8) == (0, False)
+    assert plan(1024, 1024, 1024, 4, dfft.EXCHANGE_NCCL) == (0, False)     # NCCL: opt-in
+    assert plan(1024, 1024, 1024, 4, direction=BACKWARD) == (0, False)     # backward: opt-in (two-stream schedule)
+    assert plan(1024, 1024, 1024, 4, dfft.NO_PIPELINE) == (0, False)
+    assert plan(512, 512, 512, 2, dfft.FORCE_PIPELINE) == (4, True)
+    assert plan(512, 512, 512, 4, dfft.EXCHANGE_NCCL | dfft.FORCE_PIPELINE) == (4, False)
+    assert plan(512, 512, 512, 4, dfft.FORCE_PIPELINE, BACKWARD) == (4, False)
+    assert plan(64, 512, 512, 4, dfft.FORCE_PIPELINE) == (4, False)        # not a cube: two streams
+    assert plan(512, 512, 512, 1, dfft.FORCE_PIPELINE) == (0, False)
+    monkeypatch.setenv("DFFT_PIPELINE", "1")
+    assert plan(512, 512, 512, 4) == (4, True)
+    monkeypatch.setenv("DFFT_PIPE_MODE", "streams")
+    assert plan(512, 512, 512, 4) == (4, False)
+    monkeypatch.setenv("DFFT_PIPELINE", "0")
+    assert plan(1024, 1024, 1024, 8) == (0, False)
