@@ -89,6 +89,12 @@ WORKER = textwrap.dedent(r'''
         drive(8, 128, 128, P, dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE)     # stream-pipelined (4 z-parts, two streams), fused part 0
         drive(8, 12, 128, P, dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE)      # ... two-sweep t0
         drive(8, 128, 128, P, dfft.EXCHANGE_P2P | dfft.NO_PIPELINE)
+        drive(128, 128, 128, P, dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE, executes=2)   # cube: the kernel chain [Z+Y0][Y1+X0]..[X last] forward
+    # 8 device-threads (the reference's largest node): plain, two-sweep, kernel chain, uneven split
+    for flags in (dfft.EXCHANGE_P2P, dfft.EXCHANGE_P2P | dfft.NO_FUSE, dfft.EXCHANGE_STAGED):
+        drive(64, 64, 64, 8, flags, executes=2)
+    drive(128, 128, 128, 8, dfft.EXCHANGE_P2P | dfft.FORCE_PIPELINE, executes=2)
+    drive(30, 22, 24, 8, dfft.EXCHANGE_P2P, executes=2)
     # the host-buffer entry points and the lines engine
     cnt = 16 * 16 * 16
     buf = dfft.fft_mpi_alloc_local_memory(cnt, dfft.ALLOC_DEV)
@@ -135,3 +141,31 @@ def test_non_dry_plans_run_to_completion_on_a_fake_runtime(fake_lib, tmp_path):
     r = subprocess.run([sys.executable, str(script), ROOT, fake_lib], capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "fakecuda control flow ok" in r.stdout
+
+
+DRIVER_SRC = os.path.join(PKG, "driver", "distFFT.cpp")
+
+
+@pytest.mark.parametrize("P", [1, 2, 8])
+def test_reference_driver_through_the_cxx_shim_on_a_fake_runtime(fake_lib, tmp_path, P):
+    """The reference-facing C++ surface (include/fft_mpi_3d_api.h: fft_mpi_init, getMaxDataCount, fft_mpi_alloc_local_memory,
+    fft_mpi_plan_dft_c2c_3d, fft_mpi_execute_dft_3d_c2c, fft_mpi_destroy_plan -- api.h:68-74) driven by driver/distFFT.cpp (the
+    call sequence of fftSpeed3d_c2c.cpp:42-138, one host thread per device like its OpenMP region) against the fake-runtime
+    build: the whole program runs to its report block without a GPU.  Numbers are meaningless here (kernels are no-ops);
+    the control flow, the printed surface and the exit code are what is checked."""
+    exe = tmp_path / "distFFT_fake"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", DRIVER_SRC, "-o", str(exe),
+                    fake_lib, "-Wl,-rpath," + os.path.dirname(fake_lib), "-lpthread"], check=True)
+    env = dict(os.environ, FAKECUDA_DEVICES="8")
+    r = subprocess.run([str(exe), "32", "32", "32", str(P)], capture_output=True, text=True, timeout=60, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert "allocate %d devices to node 0" % P in out                     # api.cpp:270
+    assert out.count("data count in device") == P                          # api.cpp:285
+    assert out.count("t0: ") >= 4 * P                                      # one stage line per forward execute and device (api.cpp:201)
+    for key in ("distributed FFT performance test", "Size:             32x32x32", "MPI ranks:        %d" % P, "Forward FFT time:", "Performance:",
+                "Max error:"):                                             # drv.cpp:126-138
+        assert key in out, key
+    # the reference's argument check (drv.cpp:33-36)
+    r = subprocess.run([str(exe), "32", "32"], capture_output=True, text=True, timeout=60, env=env)
+    assert r.returncode != 0 and "The format of arguments should be [NX, NY, NZ, GPU_COUNT]!" in r.stdout
