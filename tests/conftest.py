@@ -25,7 +25,14 @@ def n_gpus():
     return _n_gpus()
 
 
+# `-m gpu -x` order: the watchdogged smoke case, then the single-GPU product-path parity tests, then the full-size baseline
+# configurations, then the multi-GPU suites (which skip on a smaller box) -- a failure late in the list cannot hide the
+# results of the tests every box can run
+GPU_FILE_ORDER = {"test_gpu_00_smoke.py": 1, "test_gpu_parity.py": 2, "test_gpu_baseline_configs.py": 3, "test_gpu_multi.py": 4}
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda it: GPU_FILE_ORDER.get(os.path.basename(str(it.fspath)), 0))   # stable: order inside a file is kept
     # `-m gpu` on a box without a GPU must fail loudly rather than skip silently; plain runs
     # (no -m) on a CPU box skip GPU tests.
     if _n_gpus() == 0 and "gpu" not in (config.getoption("-m") or ""):

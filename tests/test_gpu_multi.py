@@ -209,7 +209,12 @@ def test_process_per_gpu_bootstrap(tmp_path, mode):
         assert f"rank {k} ok" in r.stdout
 
 
-@pytest.mark.parametrize("P,n", [(2, 64), (4, 64), (8, 64), (2, 128), (2, 256), (8, 256)])
+# the 8-device cases of this EXPERIMENTAL (non-default) kernel have not been on an 8-GPU box yet (none could be had in round 2):
+# they stay opt-in so that a surprise there cannot stop `pytest -x` before the product-path tests that sort after this file
+NOT_ON_8_YET = pytest.mark.skipif(os.environ.get("DFFT_TEST_EXPERIMENTAL") != "1", reason="experimental kernel, 8-device case not yet run on hardware: set DFFT_TEST_EXPERIMENTAL=1")
+
+
+@pytest.mark.parametrize("P,n", [(2, 64), (4, 64), pytest.param(8, 64, marks=NOT_ON_8_YET), (2, 128), (2, 256), pytest.param(8, 256, marks=NOT_ON_8_YET)])
 def test_overlapped_forward_matches_default_path(P, n):
     """DFFT_OVERLAP_X (fft_fused3_kernel: Z + Y/peer-store + X roles of all z-parts from one ticket stream, per-part arrival
     flags published once per CTA and part) must produce the same y-slabs as the plain P2P path, bit for bit, over repeated
