@@ -123,6 +123,11 @@ def run_alltoall(fp, dev, op):
 
 
 def check(n0, n1, n2, P, direction, flags, precision=dfft.DOUBLE, mutate=None):
+    need = 10 * n0 * n1 * n2            # one byte per element for ~4 buffers x (written + per-pass counts), all devices
+    if need > 2 ** 30:
+        import psutil
+        if psutil.virtual_memory().available < 2 * need:
+            pytest.skip(f"needs ~{need >> 30} GiB of host memory for the footprint maps")
     g = SlabGeometry(n0, n1, n2, P)
     fp = Footprints(g, 16 if precision == dfft.DOUBLE else 8)
     plans, ops = [], []
