@@ -48,6 +48,32 @@ def test_slab_bookkeeping_matches_oracle():
                     assert mine[k] == list(ref[k]), (k, d, direction)
 
 
+def test_slab_bookkeeping_random_geometries_match_oracle():
+    """300 random (N0, N1, N2, P <= 8) incl. every kind of short last slab: counts, local sizes and the four exchange-table
+    columns (api.cpp:84-133, 289-316) equal the oracle's restatement for every device and both directions."""
+    import numpy as np
+    co = COracle()
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(300):
+        P = int(rng.integers(1, 9))
+        n0, n1, n2 = (int(rng.integers(1, 97)) for _ in range(3))
+        splittable = all((P - 1) * -(-n // P) < n for n in (n0, n1))
+        if not splittable:          # the reference never gets here: fft_mpi_init lowers the device count first (api.cpp:232-272)
+            continue
+        g = SlabGeometry(n0, n1, n2, P)
+        for d in range(P):
+            assert dfft.getMaxDataCount(n0, n1, n2, P, d == P - 1) == co.lib.oracle_max_data_count(n0, n1, n2, P, int(d == P - 1))
+            assert dfft.fft_mpi_local_size_3d(n0, n1, n2, P, d) == (g.max_count(d), g.n0l(d), d * g.xd, g.n1l(d), d * g.yd)
+            for direction in (FORWARD, BACKWARD):
+                mine = dfft.exchange_table(n0, n1, n2, P, d, direction)
+                ref = co.exchange_table(n0, n1, n2, P, d, direction)
+                for k in ("scount", "soffset", "rcount", "roffset"):
+                    assert mine[k] == list(ref[k]), (n0, n1, n2, P, k, d, direction)
+        checked += 1
+    assert checked > 150
+
+
 def test_fft_mpi_init_device_policy():
     """getProperDeviceNum (api.cpp:232-272): without a GPU the wanted count is not clamped."""
     for n0, w in ((512, 8), (10, 4), (9, 4), (5, 4), (7, 3)):
