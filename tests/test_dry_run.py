@@ -338,6 +338,36 @@ def test_random_geometries_all_exchanges(co):
         done += 1
 
 
+def test_random_geometries_pipelined_schedules(co, monkeypatch):
+    """Seeded random sweep with DFFT_FORCE_PIPELINE: z axes long enough to be cut into parts, x / y extents even and uneven over
+    1..8 devices, P2P and NCCL, both directions, 2 or 4 parts, chain (cubes) and two-stream schedules.  Where a geometry does not
+    meet a pipeline's preconditions the plan falls back to the plain schedule -- the result must be right either way."""
+    rng = np.random.default_rng(77)
+    done = piped = 0
+    while done < 20:
+        P = int(rng.integers(2, 9))
+        n2 = int(rng.choice([64, 128]))
+        cube = done % 5 == 0
+        n0, n1 = (n2, n2) if cube else (int(x) for x in rng.choice([8, 9, 10, 12, 16, 20, 24, 30, 32, 64], 2))
+        g = SlabGeometry(n0, n1, n2, P)
+        if g.last_n0 < 1 or g.last_n1 < 1:
+            continue
+        nccl = done % 3 == 1
+        direction = FORWARD if done % 2 == 0 else BACKWARD
+        monkeypatch.setenv("DFFT_PARTS", "2" if done % 4 < 2 else "4")
+        A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+        inputs, ref = oracle(co, g, A, direction)
+        flags = (dfft.EXCHANGE_NCCL if nccl else dfft.EXCHANGE_P2P) | dfft.FORCE_PIPELINE
+        got, names, _ = simulate(n0, n1, n2, P, direction, inputs, flags)
+        scale = max(np.abs(r).max() for r in ref)
+        for d in range(P):
+            n = g.out_count(d) if direction == FORWARD else g.in_count(d)
+            assert np.abs(got[d][:n] - ref[d][:n]).max() <= 1e-11 * scale, (P, n0, n1, n2, flags, direction, d, names[d])
+        piped += len(names[0]) > 4
+        done += 1
+    assert piped >= 10, piped
+
+
 def test_default_pipeline_policy(monkeypatch):
     """Which schedule a plan picks by default (dfft_plan_c2c_3d, measured policy of DESIGN.md 5.1): the kernel chain for cubes
     with axes >= 1024 points from 4 devices on (P2P), the plain schedule everywhere else; flags and environment override."""
