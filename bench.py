@@ -307,12 +307,17 @@ def run_dfft_arm(args):
         flags |= dfft.OVERLAP_X
     if args.no_pipeline:
         flags |= dfft.NO_PIPELINE
+    # watchdog: a host-side hang in plan creation or the first executes (round 1's failure) ends the process with a traceback after
+    # 10 minutes instead of holding the box until the driver's limit; device-side waits have their own 120 s bound (SpinGuard)
+    import faulthandler
+    faulthandler.dump_traceback_later(600, exit=True)
     plan = dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, tin.data_ptr(), tout.data_ptr(), comm, rank, P, dfft.FORWARD, prec, flags)
     stream = torch.cuda.ExternalStream(plan.stream, device=dev)
 
     for _ in range(max(args.warmup, 3)):
         plan.execute()
     plan.synchronize()
+    faulthandler.cancel_dump_traceback_later()
 
     sampler = ClockSampler(local)
     barrier()
