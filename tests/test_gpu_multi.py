@@ -125,7 +125,7 @@ def test_speedtest_driver_report(P):
     need(P)
     exe = os.path.join(ROOT, "distributedfft_b200", "distFFT")
     assert os.path.exists(exe), "distFFT driver was not built (python -m distributedfft_b200.build)"
-    r = subprocess.run([exe, "64", "64", "64", str(P)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, "64", "64", "64", str(P)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert f"allocate {P} devices to node 0" in r.stdout
     assert "data count in device 0 of node 0: %d" % (64 ** 3 // P) in r.stdout
@@ -135,7 +135,7 @@ def test_speedtest_driver_report(P):
     assert m.group(1, 2, 3, 4) == ("64", "64", "64", str(P))
     assert float(m.group(7)) <= 1e-11
     sh = subprocess.run(["bash", os.path.join(ROOT, "distributedfft_b200", "speedTest.sh"), str(P), "16", "16", "16"],
-                        capture_output=True, text=True, timeout=300)
+                        capture_output=True, text=True, timeout=120)
     assert sh.returncode == 0 and REPORT.search(sh.stdout), sh.stdout + sh.stderr
     bad = subprocess.run([exe, "64", "64"], capture_output=True, text=True, timeout=60)
     assert bad.returncode != 0 and "The format of arguments should be [NX, NY, NZ, GPU_COUNT]!" in bad.stdout
