@@ -8,6 +8,13 @@ Two independent restatements of the reference's `3dmpifft_opt` path live here:
                  pocketfft for the math.  It shares no code with oracle_fft.c, so agreement of
                  the two (tests/test_oracle.py) checks both the engine and the layout maps.
 
+Both are PINNED on executed reference code (tests/test_oracle_ref3d.py, tests/test_oracle_ref.py):
+* `Ref3dmpifft` -- the reference's own 3dmpifft_opt sources (fft_mpi_3d_api.cpp, kernel_func.cpp, the cuTranspose kernels)
+                 compiled in place against a HIP-on-CPU shim (oracle/ref_3dmpifft) and run on host memory: both plan
+                 buffers after every stage, the exchange tables, the count helpers;
+* `HeffteRef`  -- the reference tree's heFFTe 2.1.0 (stock CPU backend, oracle/ref_heffte): whole 3-D spectra; also the CPU
+                 arm of bench.py.
+
 Layouts follow SURVEY.md Appendix A; reference citations are on each function
 (paths relative to /root/reference).
 """
@@ -362,3 +369,79 @@ def physical_core_cpus(allowed=None):
             seen.add(key)
             out.append(c)
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# oracle/_ref/libref3dmpifft.so: the reference's OWN HOT-PATH SOURCES executed on the CPU.  oracle/ref_3dmpifft/Makefile
+# compiles 3dmpifft_opt/include/fft_mpi_3d_api.cpp, kernel_func.cpp and fast_transpose/kernels_{201,120}.cpp where they lie
+# under /root/reference against a HIP-on-CPU shim (kernel launches run on fibers, so __shared__ / __syncthreads work); only
+# the JIT FFT engine behind templateFFT.h is replaced (by a plain DFT).  Plan creation, exchange tables, fftZY,
+# localTransposeUneven + pack kernels, slabAlltoall, fftX + cuTranspose kernels are the reference's code.
+# ------------------------------------------------------------------------------------------
+_REF3D_LIB = os.path.join(_REF_DIR, "libref3dmpifft.so")
+_REF3D_SRC = "/root/reference/3dmpifft_opt/include"
+
+
+def build_ref3d(force: bool = False):
+    """Build oracle/_ref/libref3dmpifft.so when the reference tree is present; else use the prebuilt file.  Returns its
+    path, or None when it neither exists nor can be built."""
+    rdir = os.path.join(_HERE, "ref_3dmpifft")
+    if os.path.isdir(_REF3D_SRC):
+        deps = [os.path.join(rdir, f) for f in ("ref3d_glue.cpp", "Makefile", "mpi.h", "rocfft.h", "hipfft.h", "rccl.h", "hip/hip_runtime.h", "hip/hiprtc.h")]
+        if force or not os.path.exists(_REF3D_LIB) or os.path.getmtime(_REF3D_LIB) < max(os.path.getmtime(d) for d in deps):
+            subprocess.run(["make", "-C", rdir, "-s", "REF=/root/reference"], check=True)
+    return _REF3D_LIB if os.path.exists(_REF3D_LIB) else None
+
+
+class Ref3dmpifft:
+    """ctypes binding of oracle/_ref/libref3dmpifft.so (oracle/ref_3dmpifft/ref3d_glue.cpp).  Sizes are test-sized: every GPU
+    thread of every kernel launch is a fiber and the FFT arithmetic is an O(N^2) DFT."""
+
+    def __init__(self):
+        path = build_ref3d()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libref3dmpifft.so is missing and /root/reference is not available to build it")
+        self.lib = ctypes.CDLL(path)
+        i, vp = ctypes.c_int, ctypes.c_void_p
+        self.lib.ref3d_run.argtypes = [i, i, i, i, i, vp, vp, vp, vp]
+        self.lib.ref3d_max_data_count.restype = ctypes.c_longlong
+        self.lib.ref3d_max_data_count.argtypes = [i, i, i, i, i]
+        self.lib.ref3d_proper_device_num.argtypes = [ctypes.c_longlong, i, i]
+
+    def max_data_count(self, n0, n1, n2, P, is_last):
+        """getMaxDataCount, fft_mpi_3d_api.cpp:289-316, as compiled from the reference"""
+        return int(self.lib.ref3d_max_data_count(n0, n1, n2, P, int(is_last)))
+
+    def proper_device_num(self, n0, wanted, have=64):
+        """getProperDeviceNum, fft_mpi_3d_api.cpp:232-272 (one rank, `have` devices present)"""
+        return int(self.lib.ref3d_proper_device_num(n0, wanted, have))
+
+    def tables(self, n0, n1, n2, P, direction):
+        """TransInfo of every device as filled by the reference's plan creation (fft_mpi_3d_api.cpp:84-133), no transform:
+        tables[p][q] = (scount, soffset, rcount, roffset)"""
+        t = np.zeros((P, P, 4), dtype=np.int64)
+        if self.lib.ref3d_tables(n0, n1, n2, P, direction, ctypes.c_void_p(t.ctypes.data)) != 0:
+            raise ValueError("ref3d_tables failed")
+        return t
+
+    def execute(self, geom: SlabGeometry, inputs, direction, stages: bool = False):
+        """Run the reference driver's sequence (fftSpeed3d_c2c.cpp:42-102) on P "devices".  inputs[p]: max_count(p) complex128
+        (x-slabs forward, y-slabs backward).  Returns (outputs, tables, dumps): outputs[p] = the device's out buffer,
+        tables[p][q] = (scount, soffset, rcount, roffset) of plan p towards q, dumps[p][stage] = (bufferDev1, bufferDev2)
+        after each of the four stages in execution order when stages=True (the stage functions are then called one by one),
+        else None (the reference's own fft_mpi_execute_dft_3d_c2c runs)."""
+        P = geom.P
+        ins = [np.ascontiguousarray(b, dtype=np.complex128) for b in inputs]
+        assert all(b.size == geom.max_count(p) for p, b in enumerate(ins))
+        outs = [np.zeros(geom.max_count(p), dtype=np.complex128) for p in range(P)]
+        tables = np.zeros((P, P, 4), dtype=np.int64)
+        arr = ctypes.c_void_p * P
+        dumps = dp = None
+        if stages:
+            dumps = [[(np.zeros(geom.max_count(p), dtype=np.complex128), np.zeros(geom.max_count(p), dtype=np.complex128)) for _ in range(4)] for p in range(P)]
+            dp = (ctypes.c_void_p * (P * 8))(*[dumps[p][s][w].ctypes.data for p in range(P) for s in range(4) for w in range(2)])
+        rc = self.lib.ref3d_run(geom.n0, geom.n1, geom.n2, P, direction, arr(*[b.ctypes.data for b in ins]), arr(*[b.ctypes.data for b in outs]),
+                                dp, tables.ctypes.data)
+        if rc != 0:
+            raise ValueError(f"ref3d_run failed ({rc}): the reference would not run {geom.n0}x{geom.n1}x{geom.n2} on {P} devices")
+        return outs, tables, dumps

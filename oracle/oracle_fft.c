@@ -14,7 +14,10 @@
  * Parity pin: the reference's own tests pin only the fwd+bwd round trip
  * (3dmpifft_opt/fftSpeed3d_c2c.cpp:79-91).  The 1-D engine below is pinned against the
  * golden vectors the reference tree carries (heffte/heffteBenchmark/test/test_units_nompi.cpp:92-190,
- * test_units_stock.cpp:229-255) in tests/test_oracle.py, and against numpy pocketfft.
+ * test_units_stock.cpp:229-255) in tests/test_oracle.py, and against numpy pocketfft.  The stage functions are pinned on
+ * EXECUTED reference code: tests/test_oracle_ref3d.py compares both buffers of every device after every stage with the
+ * reference's own fft_mpi_3d_api.cpp + kernel_func.cpp + cuTranspose kernels run on the CPU (oracle/ref_3dmpifft), and
+ * tests/test_oracle_ref.py compares whole spectra with the reference tree's heFFTe (oracle/ref_heffte).
  *
  * Math convention (templateFFT/src/templateFFT.cpp:5121-5141 LUT holds e^{+i theta};
  * :338 forward kernels conjugate it; :5946 normalize=0):
