@@ -372,10 +372,11 @@ def physical_core_cpus(allowed=None):
 
 
 # ------------------------------------------------------------------------------------------
-# oracle/_ref/libref3dmpifft.so: the reference's OWN HOT-PATH SOURCES executed on the CPU.  oracle/ref_3dmpifft/Makefile
-# compiles 3dmpifft_opt/include/fft_mpi_3d_api.cpp, kernel_func.cpp and fast_transpose/kernels_{201,120}.cpp where they lie
-# under /root/reference against a HIP-on-CPU shim (kernel launches run on fibers, so __shared__ / __syncthreads work); only
-# the JIT FFT engine behind templateFFT.h is replaced (by a plain DFT).  Plan creation, exchange tables, fftZY,
+# oracle/_ref/libref3dmpifft.so (+ libtemplatefft_cpu.so, libhipcpu.so): the reference's OWN HOT-PATH SOURCES executed on the
+# CPU.  oracle/ref_3dmpifft/Makefile compiles 3dmpifft_opt/include/fft_mpi_3d_api.cpp, kernel_func.cpp,
+# fast_transpose/kernels_{201,120}.cpp and the FFT engine templateFFT/src/templateFFT.cpp where they lie under /root/reference
+# against a HIP-on-CPU shim (kernel launches run on fibers, so __shared__ / __syncthreads work; the kernels the engine generates
+# at run time are compiled with g++ in place of hiprtc).  Plan creation, exchange tables, fftZY, the FFT kernels,
 # localTransposeUneven + pack kernels, slabAlltoall, fftX + cuTranspose kernels are the reference's code.
 # ------------------------------------------------------------------------------------------
 _REF3D_LIB = os.path.join(_REF_DIR, "libref3dmpifft.so")
@@ -387,8 +388,10 @@ def build_ref3d(force: bool = False):
     path, or None when it neither exists nor can be built."""
     rdir = os.path.join(_HERE, "ref_3dmpifft")
     if os.path.isdir(_REF3D_SRC):
-        deps = [os.path.join(rdir, f) for f in ("ref3d_glue.cpp", "Makefile", "mpi.h", "rocfft.h", "hipfft.h", "rccl.h", "hip/hip_runtime.h", "hip/hiprtc.h")]
-        if force or not os.path.exists(_REF3D_LIB) or os.path.getmtime(_REF3D_LIB) < max(os.path.getmtime(d) for d in deps):
+        deps = [os.path.join(rdir, f) for f in ("ref3d_glue.cpp", "hipcpu.cpp", "tfft_engine.cpp", "Makefile", "mpi.h", "rocfft.h", "hipfft.h", "rccl.h",
+                                                "hip/hip_runtime.h", "hip/hiprtc.h")]
+        libs = [_REF3D_LIB, os.path.join(_REF_DIR, "libhipcpu.so"), os.path.join(_REF_DIR, "libtemplatefft_cpu.so")]
+        if force or not all(os.path.exists(l) for l in libs) or min(os.path.getmtime(l) for l in libs) < max(os.path.getmtime(d) for d in deps):
             subprocess.run(["make", "-C", rdir, "-s", "REF=/root/reference"], check=True)
     return _REF3D_LIB if os.path.exists(_REF3D_LIB) else None
 
@@ -407,6 +410,42 @@ class Ref3dmpifft:
         self.lib.ref3d_max_data_count.restype = ctypes.c_longlong
         self.lib.ref3d_max_data_count.argtypes = [i, i, i, i, i]
         self.lib.ref3d_proper_device_num.argtypes = [ctypes.c_longlong, i, i]
+        self.lib.ref3d_set_engine.argtypes = [i]
+        self.lib.ref3d_engine_fft.argtypes = [i, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, i, vp]
+        self.engine = self.set_engine("templatefft")
+
+    def set_engine(self, name: str) -> str:
+        """'templatefft': the reference's own FFT engine (templateFFT/src/templateFFT.cpp: its generator and the kernels it emits,
+        compiled with g++ at run time; needs g++); 'dft': a plain DFT behind the same entry points.  Returns the engine in effect
+        ('dft' when libtemplatefft_cpu.so is absent)."""
+        got = self.lib.ref3d_set_engine(1 if name == "templatefft" else 0)
+        self.engine = "templatefft" if got == 1 else "dft"
+        return self.engine
+
+    def engine_used(self, n0, n1, n2) -> str:
+        """which FFT arithmetic execute() runs for this size"""
+        def smooth7(n):
+            for p in (2, 3, 5, 7):
+                while n % p == 0:
+                    n //= p
+            return n == 1
+        return self.engine if self.engine == "dft" or all(smooth7(n) for n in (n0, n1, n2)) else "dft"
+
+    def engine_fft(self, a: np.ndarray, fftdim: int = 1, inverse: bool = False):
+        """The reference's FFT engine alone (the templateFFT batch-test surface): transform over the last `fftdim` axes of the
+        C-ordered complex128 array `a`, leading axes are batches.  Returns the result, or None when the generator does not
+        take the size (a prime factor > 7)."""
+        x = np.ascontiguousarray(a, dtype=np.complex128).copy()
+        shp = x.shape
+        s0 = shp[-1]
+        s1 = shp[-2] if x.ndim >= 2 else 1
+        s2 = int(np.prod(shp[:-2])) if x.ndim > 2 else 1
+        rc = self.lib.ref3d_engine_fft(fftdim, s0, s1, s2, int(inverse), x.ctypes.data)
+        if rc == -3:
+            return None
+        if rc != 0:
+            raise RuntimeError(f"ref3d_engine_fft failed ({rc})")
+        return x
 
     def max_data_count(self, n0, n1, n2, P, is_last):
         """getMaxDataCount, fft_mpi_3d_api.cpp:289-316, as compiled from the reference"""

@@ -34,7 +34,18 @@ void hipcpu_syncthreads(void);
 #define __global__
 #define __device__
 #define __host__
+#define __constant__
+#define __launch_bounds__(...)
+#ifdef HIPCPU_GENERATED_KERNEL
+/* a kernel the reference's generator (templateFFT.cpp) emitted at run time, compiled by the hiprtc stand-in (tfft_engine.cpp):
+ * it declares `extern __shared__ float shared[];` -- dynamic shared memory, here 64 KB per "device" thread */
+#define __shared__ thread_local
+thread_local float shared[16384] __attribute__((aligned(16)));
+#else
 #define __shared__ static thread_local     /* one copy per "device" thread; blocks of a launch run one after the other */
+#endif
+typedef struct { double x, y; } double2;
+typedef struct { float x, y; } float2;
 
 typedef int hipError_t;
 #define hipSuccess 0
@@ -44,6 +55,10 @@ typedef void* hipCtx_t;
 typedef void* hipModule_t;
 typedef void* hipFunction_t;
 typedef void* hipDeviceptr_t;
+enum hipDeviceAttribute_t { hipDeviceAttributeMaxThreadsPerBlock, hipDeviceAttributeMaxGridDimX, hipDeviceAttributeMaxGridDimY, hipDeviceAttributeMaxGridDimZ,
+                            hipDeviceAttributeMaxBlockDimX, hipDeviceAttributeMaxBlockDimY, hipDeviceAttributeMaxBlockDimZ, hipDeviceAttributeMaxSharedMemoryPerBlock,
+                            hipDeviceAttributeWarpSize };
+enum hipFuncAttribute { hipFuncAttributeMaxDynamicSharedMemorySize };
 enum hipMemcpyKind { hipMemcpyHostToHost = 0, hipMemcpyHostToDevice = 1, hipMemcpyDeviceToHost = 2, hipMemcpyDeviceToDevice = 3, hipMemcpyDefault = 4 };
 
 #ifdef __cplusplus
@@ -64,6 +79,15 @@ hipError_t hipStreamCreate(hipStream_t* s);
 hipError_t hipStreamDestroy(hipStream_t s);
 hipError_t hipStreamSynchronize(hipStream_t s);
 hipError_t hipcpu_malloc(void** p, size_t bytes);
+/* the module API the reference's FFT engine uses after hiprtc (templateFFT.cpp:5709-5745, 6228): modules are shared objects */
+hipError_t hipDeviceGetAttribute(int* value, enum hipDeviceAttribute_t attr, int device);
+hipError_t hipModuleLoadDataEx(hipModule_t* module, const void* image, unsigned nopt, void* opts, void* vals);
+hipError_t hipModuleUnload(hipModule_t module);
+hipError_t hipModuleGetFunction(hipFunction_t* f, hipModule_t module, const char* name);
+hipError_t hipModuleGetGlobal(hipDeviceptr_t* ptr, size_t* bytes, hipModule_t module, const char* name);
+hipError_t hipFuncSetAttribute(hipFunction_t f, enum hipFuncAttribute attr, int value);
+hipError_t hipModuleLaunchKernel(hipFunction_t f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned shmem, hipStream_t s,
+                                 void** args, void** extra);
 #ifdef __cplusplus
 }
 template <class T> static inline hipError_t hipMalloc(T** p, size_t bytes) { return hipcpu_malloc((void**)p, bytes); }

@@ -5,107 +5,32 @@
 //                                               slabAlltoall, fftX, fft_mpi_execute_dft_3d_c2c, the count helpers
 //     3dmpifft_opt/include/kernel_func.cpp      the t1 pack / unpack kernels (hipLaunchKernelGGL launches)
 //     3dmpifft_opt/include/fast_transpose/kernels_201.cpp, kernels_120.cpp   the cuTranspose tile kernels of fftX
-// against the HIP-on-CPU headers of this directory.  What this file supplies in place of code that cannot run here:
-//   * the HIP runtime calls (heap memory, memcpy) and the kernel launcher: a launch runs its grid block by block on the calling
-//     thread with one ucontext fiber per GPU thread, so __shared__ tiles and __syncthreads() behave as on the device;
-//   * the four templateFFT entry points the reference calls (templateFFT.h:361-365).  The real engine JIT-compiles HIP
-//     kernels with hiprtc; here launchFFTKernel is a plain DFT with the engine's semantics: an unnormalised transform over the
-//     first FFTdim axes of `size` (axis 0 fastest), in place on *configuration.buffer as it is at launch time, every line of
-//     the remaining axes being a batch (templateFFT/src/templateFFT.cpp:6073-6095 axis 0, :6106-6109 axis 1);
+// against the HIP-on-CPU headers of this directory (runtime: hipcpu.cpp -- heap memory, memcpy, kernel launches on fibers so
+// that __shared__ tiles and __syncthreads() behave as on the device).  What this file supplies:
+//   * the four templateFFT entry points the reference calls (templateFFT.h:361-365).  Engine 1 (default): they forward to
+//     libtemplatefft_cpu.so = the reference's own FFT engine (templateFFT/src/templateFFT.cpp, compiled in place) whose
+//     run-time-generated kernels are compiled with g++ and run on fibers (tfft_engine.cpp) -- the reference's butterflies and
+//     twiddles.  Engine 0: a plain DFT with the engine's semantics: an unnormalised transform over the first FFTdim axes of
+//     `size` (axis 0 fastest), in place on *configuration.buffer as it is at launch time, every line of the remaining axes
+//     being a batch (templateFFT/src/templateFFT.cpp:6073-6095 axis 0, :6106-6109 axis 1).  The two must agree (tested);
 //   * cut_transpose3d: fast_transpose/transpose3d.cpp launches with <<< >>> and cannot go through g++, so its dispatcher is
 //     restated for the two out-of-place permutations fftX uses (transpose3d.cpp:198-224 -> 120, :225-262 -> 201, grid from
 //     set_grid_dims :312-330); the kernels it launches are the reference's;
 //   * ref3d_run(): the call sequence of the reference driver (fftSpeed3d_c2c.cpp:42-102), one OpenMP thread per device.
-// So the slab bookkeeping, the exchange tables, the pack / unpack index maps, the all-to-all offsets, the transposes and the
-// order of the stages are the reference's executed code; only the 1-D/2-D DFT arithmetic is not.
+// So with engine 1 everything that computes or moves data -- slab bookkeeping, exchange tables, FFT kernels, pack / unpack
+// maps, all-to-all offsets, transposes, stage order -- is the reference's code, executed.
+#include <dlfcn.h>
 #include <omp.h>
-#include <ucontext.h>
 
 #include <complex>
+#include <string>
 #include <vector>
 
 #include "fft_mpi_3d_api.h"          // the reference's (found through -I$(REF)/3dmpifft_opt/include)
 #include "fast_transpose/kernels_120.h"
 #include "fast_transpose/kernels_201.h"
 
-// ------------------------------------------------------------------------------------------ HIP runtime on the heap
-thread_local hipcpu_uint3 threadIdx, blockIdx;
-thread_local dim3 blockDim, gridDim;
-static int g_devices = 8;
-
-extern "C" {
-const char* hipGetErrorString(hipError_t e) { return e ? "hip-on-cpu error" : "no error"; }
-hipError_t hipGetDeviceCount(int* n) { *n = g_devices; return hipSuccess; }
-hipError_t hipSetDevice(int) { return hipSuccess; }
-hipError_t hipDeviceCanAccessPeer(int* can, int, int) { *can = 1; return hipSuccess; }
-hipError_t hipDeviceEnablePeerAccess(int, unsigned) { return hipSuccess; }
-hipError_t hipDeviceSynchronize(void) { return hipSuccess; }
-hipError_t hipcpu_malloc(void** p, size_t bytes) { *p = calloc(1, bytes ? bytes : 1); return *p ? hipSuccess : 2; }
-hipError_t hipFree(void* p) { free(p); return hipSuccess; }
-hipError_t hipMemcpy(void* d, const void* s, size_t n, enum hipMemcpyKind) { if (d != s) memmove(d, s, n); return hipSuccess; }
-hipError_t hipMemcpyAsync(void* d, const void* s, size_t n, enum hipMemcpyKind, hipStream_t) { if (d != s) memmove(d, s, n); return hipSuccess; }
-hipError_t hipMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, hipStream_t) { if (d != s) memmove(d, s, n); return hipSuccess; }
-hipError_t hipMemcpyDtoH(void* d, const void* s, size_t n) { memmove(d, s, n); return hipSuccess; }
-hipError_t hipStreamCreate(hipStream_t* s) { *s = nullptr; return hipSuccess; }
-hipError_t hipStreamDestroy(hipStream_t) { return hipSuccess; }
-hipError_t hipStreamSynchronize(hipStream_t) { return hipSuccess; }
-}
-
-// ------------------------------------------------------------------------------------------ kernel launcher (fibers)
-namespace {
-struct Fiber {
-    ucontext_t ctx;
-    std::vector<char> stack;
-    bool done;
-};
-thread_local ucontext_t t_sched;
-thread_local Fiber* t_cur = nullptr;
-thread_local const std::function<void()>* t_body = nullptr;
-thread_local std::vector<Fiber> t_fibers;
-
-void fiber_main()
-{
-    (*t_body)();
-    t_cur->done = true;
-    swapcontext(&t_cur->ctx, &t_sched);
-}
-}  // namespace
-
-void hipcpu_syncthreads(void) { swapcontext(&t_cur->ctx, &t_sched); }
-
-void hipcpu_launch(dim3 grid, dim3 block, const std::function<void()>& body)
-{
-    const size_t nt = (size_t)block.x * block.y * block.z;
-    if (t_fibers.size() < nt) t_fibers.resize(nt);
-    gridDim = grid;
-    blockDim = block;
-    t_body = &body;
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
-                blockIdx = {bx, by, bz};
-                for (size_t t = 0; t < nt; t++) {
-                    Fiber& f = t_fibers[t];
-                    if (f.stack.empty()) f.stack.resize(64 << 10);
-                    getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = f.stack.data();
-                    f.ctx.uc_stack.ss_size = f.stack.size();
-                    f.ctx.uc_link = &t_sched;
-                    makecontext(&f.ctx, fiber_main, 0);
-                    f.done = false;
-                }
-                // every sweep runs each live thread of the block up to its next __syncthreads() (or its end): a barrier
-                for (size_t live = nt; live;)
-                    for (size_t t = 0; t < nt; t++) {
-                        Fiber& f = t_fibers[t];
-                        if (f.done) continue;
-                        threadIdx = {(unsigned)(t % block.x), (unsigned)(t / block.x % block.y), (unsigned)(t / ((size_t)block.x * block.y))};
-                        t_cur = &f;
-                        swapcontext(&t_sched, &f.ctx);
-                        if (f.done) live--;
-                    }
-            }
-}
+extern "C" void hipcpu_set_device_count(int n);      // hipcpu.cpp
 
 // ------------------------------------------------------------------------------------------ the FFT engine's entry points
 typedef std::complex<double> cd;
@@ -127,17 +52,61 @@ static void dft_lines(cd* data, long n, long stride, long lines, long line_dist,
     }
 }
 
+// Engine 1 (default when oracle/_ref/libtemplatefft_cpu.so is there): the reference's own generator + generated kernels
+// (tfft_engine.cpp).  Engine 0: the plain DFT above.  The handle of engine 1 rides in app->localFFTPlan.
+static int g_engine = -1;
+static void* (*p_create)(int, long long, long long, long long, int) = nullptr;
+static int (*p_launch)(void*, void**, int) = nullptr;
+static void (*p_destroy)(void*) = nullptr;
+static bool engine_available()
+{
+    static int state = -1;
+    if (state < 0) {
+        state = 0;
+        Dl_info info;
+        if (dladdr((void*)&engine_available, &info) && info.dli_fname) {
+            std::string p(info.dli_fname);
+            const size_t k = p.rfind('/');
+            p = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/libtemplatefft_cpu.so";
+            if (void* h = dlopen(p.c_str(), RTLD_NOW | RTLD_LOCAL)) {
+                p_create = (decltype(p_create))dlsym(h, "tfft_create");
+                p_launch = (decltype(p_launch))dlsym(h, "tfft_launch");
+                p_destroy = (decltype(p_destroy))dlsym(h, "tfft_destroy");
+                state = p_create && p_launch && p_destroy;
+            }
+        }
+    }
+    return state == 1;
+}
+extern "C" int ref3d_set_engine(int e)        // 0 DFT, 1 the reference's engine; returns the engine in effect
+{
+    g_engine = (e == 1 && engine_available()) ? 1 : 0;
+    return g_engine;
+}
+static int engine() { return g_engine < 0 ? ref3d_set_engine(1) : g_engine; }
+
 FFTResult initializeFFT(FFTApplication* app, FFTConfiguration cfg)
 {
     if (cfg.FFTdim < 1 || cfg.FFTdim > 2 || !cfg.doublePrecision) return FFT_ERROR_FAILED_TO_INITIALIZE;
     app->configuration = cfg;     // (cfg.bufferSize points at a local of setFFTPlans, api.cpp:396/425: never dereferenced here)
+    app->localFFTPlan = nullptr;
+    if (engine() == 1) {
+        // null: a length the reference's generator cannot do (a prime factor > 7, tfft_engine.cpp); the DFT then stands in for this
+        // application so that the surrounding reference code (tables, pack maps, exchange) can still be exercised on such sizes
+        app->localFFTPlan = (FFTPlan*)p_create((int)cfg.FFTdim, (long long)cfg.size[0], (long long)cfg.size[1], (long long)cfg.size[2], cfg.makeInversePlanOnly ? 1 : 0);
+    }
     return FFT_SUCCESS;
 }
 FFTResult setFFTArgs(GPU*, FFTApplication*, FFTLaunchParams*, int) { return FFT_SUCCESS; }
-void deleteFFT(FFTApplication*) {}
+void deleteFFT(FFTApplication* app)
+{
+    if (app->localFFTPlan && p_destroy) p_destroy(app->localFFTPlan);
+    app->localFFTPlan = nullptr;
+}
 hipError_t launchFFTKernel(FFTApplication* app, int inverse)
 {
     const FFTConfiguration& c = app->configuration;
+    if (app->localFFTPlan) return (hipError_t)p_launch(app->localFFTPlan, c.buffer, inverse);
     cd* data = (cd*)*c.buffer;
     const long s0 = (long)c.size[0], s1 = (long)(c.size[1] ? c.size[1] : 1), s2 = (long)(c.size[2] ? c.size[2] : 1);
     // axis 0: every line of the other two axes
@@ -145,6 +114,20 @@ hipError_t launchFFTKernel(FFTApplication* app, int inverse)
     if (c.FFTdim == 2)
         for (long b = 0; b < s2; b++) dft_lines(data + b * s0 * s1, s1, s0, s0, 1, inverse != 0);
     return hipSuccess;
+}
+
+// the reference's FFT engine on its own: an in-place transform of `data` (s0 fastest) over the first fftdim axes, the other axes
+// being batches -- the templateFFT batch-test surface (templateFFT/batchTest/Test_1D.cpp, Test_2D.cpp).  -2: engine absent,
+// -3: the generator refuses the size
+extern "C" int ref3d_engine_fft(int fftdim, long long s0, long long s1, long long s2, int inverse, double* data)
+{
+    if (!engine_available()) return -2;
+    void* h = p_create(fftdim, s0, s1, s2, inverse);
+    if (!h) return -3;
+    void* buf = data;
+    const int rc = p_launch(h, &buf, inverse);
+    p_destroy(h);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------ cuTranspose dispatcher (restated)
@@ -175,7 +158,7 @@ extern "C" int ref3d_run(int n0, int n1, int n2, int P, int direction, const dou
                          long long* tables /* P * P * 4: scount, soffset, rcount, roffset of every device, or null */)
 {
     if (P < 1 || P > 64 || (direction != FORWARD && direction != BACKWARD)) return -1;
-    g_devices = P;
+    hipcpu_set_device_count(P);
     const longInt64 N[3] = {n0, n1, n2};
     int newCount = 0, newCountInNode = 0;
     std::vector<longInt64> dataCount(P);
@@ -231,6 +214,8 @@ extern "C" int ref3d_run(int n0, int n1, int n2, int P, int direction, const dou
             }
 #pragma omp barrier
             memcpy(out[i], outDev, (size_t)maxc * sizeof(Complex));     // bufferDev2 == outDev (api.cpp:68-75)
+            deleteFFT(&plan->appYZ);          // (fft_mpi_destroy_plan, api.cpp:143-179, leaves the two FFT applications behind)
+            deleteFFT(&plan->appX);
             fft_mpi_destroy_plan(plan);
             hipFree(inDev);
             hipFree(outDev);
@@ -243,7 +228,7 @@ extern "C" int ref3d_run(int n0, int n1, int n2, int P, int direction, const dou
 extern "C" int ref3d_tables(int n0, int n1, int n2, int P, int direction, long long* tables)
 {
     if (P < 1 || P > 64) return -1;
-    g_devices = P;
+    hipcpu_set_device_count(P);
     std::vector<Complex*> node_data(P, nullptr);
     for (int i = 0; i < P; i++) {
         const longInt64 maxc = getMaxDataCount(n0, n1, n2, P, i == P - 1);
@@ -253,6 +238,8 @@ extern "C" int ref3d_tables(int n0, int n1, int n2, int P, int direction, long l
             long long* t = tables + ((size_t)i * P + q) * 4;
             t[0] = plan->tInfo.scount[q]; t[1] = plan->tInfo.soffset[q]; t[2] = plan->tInfo.rcount[q]; t[3] = plan->tInfo.roffset[q];
         }
+        deleteFFT(&plan->appYZ);
+        deleteFFT(&plan->appX);
         fft_mpi_destroy_plan(plan);
         hipFree(inDev);
     }
@@ -263,7 +250,7 @@ extern "C" int ref3d_tables(int n0, int n1, int n2, int P, int direction, long l
 extern "C" long long ref3d_max_data_count(int n0, int n1, int n2, int P, int is_last) { return getMaxDataCount(n0, n1, n2, P, is_last != 0); }
 extern "C" int ref3d_proper_device_num(long long n0, int wanted, int have)
 {
-    g_devices = have;
+    hipcpu_set_device_count(have);
     const longInt64 N[3] = {n0, 1, 1};
     int total = 0, in_node = 0;
     getProperDeviceNum(N, wanted, 1, 0, total, in_node);

@@ -1,9 +1,11 @@
 """Pins the oracle -- stage by stage -- on the reference's OWN HOT-PATH CODE, executed.
 
 oracle/ref_3dmpifft compiles 3dmpifft_opt/include/fft_mpi_3d_api.cpp (plan creation, TransInfo tables, fftZY,
-localTransposeUneven, slabAlltoall, fftX, fft_mpi_execute_dft_3d_c2c), kernel_func.cpp (the pack / unpack kernels) and
-fast_transpose/kernels_{201,120}.cpp (the cuTranspose tile kernels) from /root/reference, in place, against a HIP-on-CPU shim
-and runs them on host memory (GPU threads are fibers; only the JIT FFT engine is replaced, by a DFT).
+localTransposeUneven, slabAlltoall, fftX, fft_mpi_execute_dft_3d_c2c), kernel_func.cpp (the pack / unpack kernels),
+fast_transpose/kernels_{201,120}.cpp (the cuTranspose tile kernels) and the FFT engine templateFFT/src/templateFFT.cpp (the
+kernel generator) from /root/reference, in place, against a HIP-on-CPU shim and runs them on host memory: GPU threads are
+fibers, and the kernels the engine generates at run time are compiled with g++ in place of hiprtc -- so the butterflies and
+twiddles that run are the reference's too.
 
 * committed vectors (tests/golden/ref3d_vectors.json, made by tests/golden/make_ref3d_vectors.py in the build container):
   BOTH plan buffers of every device after EVERY stage, the outputs and the exchange tables -- compared with both
@@ -42,7 +44,8 @@ def c(v):
 
 
 def test_both_restatements_match_the_executed_reference_at_every_stage_boundary(co, gold):
-    assert "fft_mpi_3d_api.cpp" in gold["library"] and "kernel_func.cpp" in gold["library"]
+    assert "fft_mpi_3d_api.cpp" in gold["library"] and "kernel_func.cpp" in gold["library"] and "templateFFT.cpp" in gold["library"]
+    assert gold["engine"] == "templatefft"        # the vectors come from the reference's own generated FFT kernels
     for case in gold["cases"]:
         n0, n1, n2 = case["shape"]
         P, direction = case["devices"], case["direction"]
@@ -178,3 +181,100 @@ def test_live_counts_and_policy_sweep(ref):
     for n0 in range(1, 70):
         for w in range(1, 9):
             assert proper_device_num(n0, w) == ref.proper_device_num(n0, w), (n0, w)
+
+
+def test_oracle_engine_matches_the_references_generated_fft_kernels(co, gold):
+    """The 1-D / 2-D engine alone, on the baseline's axis lengths (512, 768, 1024 among them): oracle_fft.c's Stockham engine and
+    numpy against what the reference's generated kernels produced (committed vectors)."""
+    for case in gold["engine_cases"]:
+        x = c(case["input"]).reshape(case["shape"])
+        n = x.size
+        tol = 1e-15 * 8 * np.log2(n) * np.abs(c(case["forward"])).max()
+        if case["fftdim"] == 1:
+            mine = co.fft_axis(x.reshape(1, -1), 1, -1).reshape(-1)
+            npy = np.fft.fft(x)
+        else:
+            mine = co.fft_axis(co.fft_axis(x, 1, -1), 0, -1).reshape(-1)
+            npy = np.fft.fft2(x).reshape(-1)
+        assert np.abs(mine - c(case["forward"])).max() <= tol, case["shape"]
+        assert np.abs(npy.reshape(-1) - c(case["forward"])).max() <= tol, case["shape"]
+        if "backward" in case:
+            if case["fftdim"] == 1:
+                mine = co.fft_axis(x.reshape(1, -1), 1, +1).reshape(-1)
+            else:
+                mine = co.fft_axis(co.fft_axis(x, 1, +1), 0, +1).reshape(-1)
+            assert np.abs(mine - c(case["backward"])).max() <= tol, case["shape"]      # unnormalised inverse (templateFFT.cpp:5946 normalize = 0)
+
+
+def test_live_reference_engine_lengths_vs_oracle_numpy_and_the_products_length_policy(co, ref):
+    """Every length the reference's generator takes up to 4096 in a sample, plus 8192 (its multi-upload path): the generated
+    kernels vs numpy and vs oracle_fft.c; the product library supports (dfft_length_kind != 0) every such length up to its
+    single-line limit -- it is a superset (radix 11 and 13 are extra)."""
+    if ref.set_engine("templatefft") != "templatefft":
+        pytest.skip("libtemplatefft_cpu.so not built")
+    rng = np.random.default_rng(11)
+    lengths = [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 24, 25, 27, 28, 30, 32, 35, 36, 48, 49, 64, 81, 96, 100, 125, 128, 243, 256, 343, 512, 625, 768,
+               1000, 1024, 2048, 4096, 8192]
+    for n in lengths:
+        a = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+        got = ref.engine_fft(a)
+        assert got is not None, n
+        want = np.fft.fft(a, axis=1)
+        assert np.abs(got - want).max() <= 1e-15 * 8 * np.log2(n) * np.abs(want).max(), n
+        if n <= 4096:
+            assert np.abs(co.fft_axis(a, 1, -1) - got).max() <= 1e-15 * 8 * np.log2(n) * np.abs(want).max(), n
+            assert dfft.length_kind(n) != 0, n
+        back = ref.engine_fft(got, inverse=True)
+        assert np.abs(back / n - a).max() <= 1e-13
+    for n in (11, 13, 17, 22, 26, 33):            # the reference's generator has no radix above 8; the product adds 11 and 13
+        assert ref.engine_fft(np.zeros(n, dtype=np.complex128)) is None
+    assert dfft.length_kind(11) != 0 and dfft.length_kind(26) != 0 and dfft.length_kind(17) == 0
+    # a 2-D plane (the fftZY configuration: size = {N2, N1}, fft_mpi_3d_api.cpp:381-384)
+    a = rng.standard_normal((3, 12, 16)) + 1j * rng.standard_normal((3, 12, 16))
+    assert np.abs(ref.engine_fft(a, 2) - np.fft.fft2(a)).max() <= 1e-13
+
+
+def test_live_both_engines_agree_on_the_whole_path(ref):
+    """The DFT stand-in (used only for sizes with a prime factor above 7, which the reference's generator cannot do) and the
+    reference's generated kernels give the same slabs."""
+    if ref.set_engine("templatefft") != "templatefft":
+        pytest.skip("libtemplatefft_cpu.so not built")
+    rng = np.random.default_rng(12)
+    for (P, n0, n1, n2) in [(2, 8, 8, 8), (3, 10, 9, 4), (4, 12, 10, 8)]:
+        g = SlabGeometry(n0, n1, n2, P)
+        A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+        for direction in (FORWARD, BACKWARD):
+            ins = _inputs(g, A, direction)
+            assert ref.set_engine("templatefft") == "templatefft" and ref.engine_used(n0, n1, n2) == "templatefft"
+            a, _, _ = ref.execute(g, ins, direction)
+            assert ref.set_engine("dft") == "dft"
+            b, _, _ = ref.execute(g, ins, direction)
+            ref.set_engine("templatefft")
+            for p in range(P):
+                assert 0 < np.abs(a[p] - b[p]).max() <= 1e-12       # different arithmetic, same transform
+
+
+@pytest.mark.parametrize("P", [1, 4])
+def test_live_baseline_config_c1_on_the_executed_reference(co, ref, P):
+    """BASELINE.json configs[0]: 64x64x64 C2C forward + inverse with the round-trip max-error check of the reference driver
+    (fftSpeed3d_c2c.cpp:79-91: |x - ifft(fft(x)) / N^3| <= 1e-11) -- run on the reference's own code (its generated FFT kernels
+    included), and the forward spectrum compared with the oracle's and numpy's."""
+    ref.set_engine("templatefft")
+    n = 64
+    g = SlabGeometry(n, n, n, P)
+    a = np.zeros(n * n * n, dtype=np.complex128)
+    co.fill_minstd(a, 4242)
+    A = a.reshape(n, n, n)
+    ins = NumpySlab(n, n, n, P).scatter_input(A)
+    spec, _, _ = ref.execute(g, ins, FORWARD)
+    b1 = [b.copy() for b in ins]
+    b2 = [np.zeros_like(b) for b in ins]
+    co.slab_execute(g, b1, b2, FORWARD)
+    F = np.fft.fftn(A)
+    for q in range(P):
+        want = F[:, q * g.yd: q * g.yd + g.n1l(q), :].transpose(1, 2, 0).reshape(-1)
+        assert np.abs(spec[q] - want).max() <= 1e-12 * 18 * np.abs(F).max()
+        assert np.abs(spec[q] - b2[q]).max() <= 1e-12 * 18 * np.abs(F).max()
+    back, _, _ = ref.execute(g, spec, BACKWARD)
+    for p in range(P):
+        assert np.abs(back[p] / n ** 3 - ins[p]).max() <= 1e-11
