@@ -390,7 +390,7 @@ def build_ref3d(force: bool = False):
     if os.path.isdir(_REF3D_SRC):
         deps = [os.path.join(rdir, f) for f in ("ref3d_glue.cpp", "hipcpu.cpp", "tfft_engine.cpp", "Makefile", "mpi.h", "rocfft.h", "hipfft.h", "rccl.h",
                                                 "hip/hip_runtime.h", "hip/hiprtc.h")]
-        libs = [_REF3D_LIB, os.path.join(_REF_DIR, "libhipcpu.so"), os.path.join(_REF_DIR, "libtemplatefft_cpu.so")]
+        libs = [_REF3D_LIB, os.path.join(_REF_DIR, "libhipcpu.so"), os.path.join(_REF_DIR, "libtemplatefft_cpu.so"), os.path.join(_REF_DIR, "distFFT_ref")]
         if force or not all(os.path.exists(l) for l in libs) or min(os.path.getmtime(l) for l in libs) < max(os.path.getmtime(d) for d in deps):
             subprocess.run(["make", "-C", rdir, "-s", "REF=/root/reference"], check=True)
     return _REF3D_LIB if os.path.exists(_REF3D_LIB) else None

@@ -75,6 +75,7 @@ hipError_t hipMemcpy(void* dst, const void* src, size_t bytes, enum hipMemcpyKin
 hipError_t hipMemcpyAsync(void* dst, const void* src, size_t bytes, enum hipMemcpyKind kind, hipStream_t s);
 hipError_t hipMemcpyPeerAsync(void* dst, int dstDev, const void* src, int srcDev, size_t bytes, hipStream_t s);
 hipError_t hipMemcpyDtoH(void* dst, const void* src, size_t bytes);
+hipError_t hipMemcpyHtoD(void* dst, const void* src, size_t bytes);
 hipError_t hipStreamCreate(hipStream_t* s);
 hipError_t hipStreamDestroy(hipStream_t s);
 hipError_t hipStreamSynchronize(hipStream_t s);

@@ -29,6 +29,7 @@ hipError_t hipMemcpy(void* d, const void* s, size_t n, enum hipMemcpyKind) { if 
 hipError_t hipMemcpyAsync(void* d, const void* s, size_t n, enum hipMemcpyKind, hipStream_t) { if (d != s) memmove(d, s, n); return hipSuccess; }
 hipError_t hipMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, hipStream_t) { if (d != s) memmove(d, s, n); return hipSuccess; }
 hipError_t hipMemcpyDtoH(void* d, const void* s, size_t n) { memmove(d, s, n); return hipSuccess; }
+hipError_t hipMemcpyHtoD(void* d, const void* s, size_t n) { memmove(d, s, n); return hipSuccess; }
 hipError_t hipStreamCreate(hipStream_t* s) { *s = nullptr; return hipSuccess; }
 hipError_t hipStreamDestroy(hipStream_t) { return hipSuccess; }
 hipError_t hipStreamSynchronize(hipStream_t) { return hipSuccess; }
