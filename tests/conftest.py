@@ -28,7 +28,8 @@ def n_gpus():
 # `-m gpu -x` order: the watchdogged smoke case, then the single-GPU product-path parity tests, then the full-size baseline
 # configurations, then the multi-GPU suites (which skip on a smaller box) -- a failure late in the list cannot hide the
 # results of the tests every box can run
-GPU_FILE_ORDER = {"test_gpu_00_smoke.py": 1, "test_gpu_parity.py": 2, "test_gpu_baseline_configs.py": 3, "test_gpu_multi.py": 4}
+GPU_FILE_ORDER = {"test_gpu_00_smoke.py": 1, "test_gpu_parity.py": 2, "test_gpu_baseline_configs.py": 3, "test_gpu_multi.py": 4,
+                  "test_gpu_zz_reference_golden.py": 5}
 
 
 def pytest_collection_modifyitems(config, items):

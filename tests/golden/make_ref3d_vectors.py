@@ -73,6 +73,16 @@ def main():
                      "tables[p][q] = [scount, soffset, rcount, roffset]",
            "input": "std::minstd_rand(4242)-style U(0,1) real and imaginary parts (oracle.minstd_uniform), world order, one stream across the cases",
            "cases": cases, "table_cases": table_cases, "device_policy": policy, "engine_cases": engine_cases}
+    # one oracle-sized 3-D case for the GPU test (binary, the JSON would be 0.5 MB): 8 x 16 x 32 on one device, input, forward
+    # output ([y][z][x]) and the unnormalised backward transform of that output, all from the reference's executed code
+    n0, n1, n2 = 8, 16, 32
+    g = SlabGeometry(n0, n1, n2, 1)
+    vals, state = minstd_uniform(2 * n0 * n1 * n2, state)
+    x = vals[0::2] + 1j * vals[1::2]
+    fwd, _, _ = ref.execute(g, [x], FORWARD)
+    bwd, _, _ = ref.execute(g, [fwd[0]], BACKWARD)
+    assert ref.engine_used(n0, n1, n2) == "templatefft"
+    np.savez(os.path.join(ROOT, "tests", "golden", "ref3d_case_8x16x32.npz"), shape=np.array([n0, n1, n2]), input=x, forward=fwd[0], backward=bwd[0])
     out = os.path.join(ROOT, "tests", "golden", "ref3d_vectors.json")
     with open(out, "w") as f:
         json.dump(doc, f)

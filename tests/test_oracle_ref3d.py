@@ -84,6 +84,21 @@ def test_both_restatements_match_the_executed_reference_at_every_stage_boundary(
                 assert np.abs(c(case["outputs"][q])[: ref.size] - ref).max() <= TOL * 10
 
 
+def test_binary_fixture_of_the_gpu_test_matches_the_oracle(co):
+    """tests/golden/ref3d_case_8x16x32.npz (what tests/test_gpu_zz_reference_golden.py holds the CUDA path against): the
+    oracle reproduces the executed reference's forward and backward outputs."""
+    z = np.load(os.path.join(HERE, "golden", "ref3d_case_8x16x32.npz"))
+    n0, n1, n2 = (int(v) for v in z["shape"])
+    g = SlabGeometry(n0, n1, n2, 1)
+    for src, want, direction in ((z["input"], z["forward"], FORWARD), (z["forward"], z["backward"], BACKWARD)):
+        b1 = [src.copy()]
+        b2 = [np.zeros_like(src)]
+        co.slab_execute(g, b1, b2, direction)
+        assert np.abs(b2[0] - want).max() <= 1e-13 * np.log2(src.size) * np.abs(want).max()
+    assert np.abs(z["forward"] - np.fft.fftn(z["input"].reshape(n0, n1, n2)).transpose(1, 2, 0).reshape(-1)).max() <= 1e-12
+    assert np.abs(z["backward"] / z["input"].size - z["input"]).max() <= 1e-13
+
+
 def test_exchange_tables_counts_and_device_policy_match_the_executed_reference(co, gold):
     """Integers, so exact: the oracle's AND the product library's TransInfo tables (dfft_exchange_table), getMaxDataCount
     (dfft_max_data_count) and the device-count policy (dfft_init) against what the reference's own functions returned."""
