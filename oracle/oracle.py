@@ -422,6 +422,14 @@ class Ref3dmpifft:
         self.engine = "templatefft" if got == 1 else "dft"
         return self.engine
 
+    def engine_schedule(self, n):
+        """(radices, uploads) the reference's generator chose for n points (templateFFT.cpp FFTScheduler), or None when it does
+        not take the length"""
+        r = (ctypes.c_int * 64)()
+        up = ctypes.c_int(0)
+        k = self.lib.ref3d_engine_schedule(ctypes.c_longlong(n), r, 64, ctypes.byref(up))
+        return None if k < 0 else (list(r[:k]), int(up.value))
+
     def engine_used(self, n0, n1, n2) -> str:
         """which FFT arithmetic execute() runs for this size"""
         def smooth7(n):

@@ -43,6 +43,10 @@ typedef long long i64;
  * 2s into an 8, then two 2s into a 4; :4580-4588 orders stages by descending radix.
  * Returns the number of stages, 0 if N has a prime factor > 13 (the reference returns
  * FFT_ERROR_UNSUPPORTED_RADIX there, templateFFT.cpp:3964).
+ * Checked against the EXECUTED generator (tests/test_oracle_ref3d.py, oracle/ref_3dmpifft): exact for powers of 2, 3, 5 and 7
+ * (512 = 8.8.8, 1024 = 8.8.8.2, ...); for mixed lengths the generator applies the :4540-4550 merge only when the per-thread
+ * register count of the other radix is a multiple of 8 / 4 (768 = 4.4.4.4.3 there, 8.8.4.3 here) and it has no radix 11 / 13
+ * kernels.  The schedule changes the rounding, not the transform; the values are compared with the generated kernels' outputs.
  * ---------------------------------------------------------------------------------------- */
 int oracle_radix_schedule(int n, int *radix)
 {

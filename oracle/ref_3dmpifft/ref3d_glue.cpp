@@ -130,6 +130,18 @@ extern "C" int ref3d_engine_fft(int fftdim, long long s0, long long s1, long lon
     return rc;
 }
 
+extern "C" int ref3d_engine_schedule(long long n, int* radices, int max_radices, int* uploads)
+{
+    if (!engine_available()) return -2;
+    static int (*p_sched)(long long, int*, int, int*) = nullptr;
+    if (!p_sched) {
+        Dl_info info;
+        dladdr((void*)p_create, &info);
+        if (void* h = dlopen(info.dli_fname, RTLD_NOW | RTLD_NOLOAD)) p_sched = (decltype(p_sched))dlsym(h, "tfft_schedule");
+    }
+    return p_sched ? p_sched(n, radices, max_radices, uploads) : -2;
+}
+
 // ------------------------------------------------------------------------------------------ cuTranspose dispatcher (restated)
 extern "C" int cut_transpose3d(data_t* output, const data_t* input, const int* size, const int* permutation, int elements_per_thread)
 {

@@ -139,6 +139,22 @@ int tfft_launch(void* handle, void** buffer, int inverse)
     h->app.configuration.buffer = buffer;                 // api.cpp:502 / :517: the buffer is re-pointed before every launch
     return (int)launchFFTKernel(&h->app, inverse);
 }
+void tfft_destroy(void* handle);
+// the radix schedule the generator chose for a 1-D transform of n points: radices of upload 0, then of upload 1, ... (one upload
+// = one kernel; more than one = the four-step path for lengths beyond a shared-memory line); *uploads gets their number
+int tfft_schedule(long long n, int* radices, int max_radices, int* uploads)
+{
+    tfft_handle* h = (tfft_handle*)tfft_create(1, n, 1, 1, 0);
+    if (!h) return -1;
+    FFTPlan* plan = h->app.localFFTPlan;
+    int k = 0;
+    *uploads = (int)plan->numAxisUploads[0];
+    for (uint64_t u = 0; u < plan->numAxisUploads[0]; u++)
+        for (uint64_t i = 0; i < plan->axes[0][u].layout.numStages && k < max_radices; i++) radices[k++] = (int)plan->axes[0][u].layout.stageRadix[i];
+    tfft_destroy(h);
+    return k;
+}
+
 void tfft_destroy(void* handle)
 {
     if (!handle) return;

@@ -160,9 +160,10 @@ def test_bootstrap_comm_world2_gloo(tmp_path):
 
 
 def test_length_policy_matches_the_reference_generator():
-    """Lengths: tuned table, run-time-scheduled 2..13-smooth lengths with the reference's radix policy
-    (templateFFT.cpp:3956-3963 factor over 2..13, :4540-4550 merge 2s into 8s then 4s, :4580-4588 descending order --
-    restated independently in oracle_fft.c), everything else rejected."""
+    """Lengths: tuned table, run-time-scheduled 2..13-smooth lengths with the radix policy restated in oracle_fft.c from
+    templateFFT.cpp:3956-3963 (factor over 2..13), :4540-4550 (merge 2s into 8s then 4s), :4580-4588 (descending order),
+    everything else rejected.  (Against the EXECUTED generator -- tests/test_oracle_ref3d.py -- that restatement is exact for
+    powers of 2, 3, 5, 7; for mixed lengths the generator merges the 2s only when its register counts allow it.)"""
     co = COracle()
     for n in (512, 768, 1024, 64, 100):
         assert dfft.length_kind(n) == 2 and dfft.length_kind(n, dfft.FLOAT) == 2

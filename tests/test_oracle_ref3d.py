@@ -293,3 +293,25 @@ def test_live_baseline_config_c1_on_the_executed_reference(co, ref, P):
     back, _, _ = ref.execute(g, spec, BACKWARD)
     for p in range(P):
         assert np.abs(back[p] / n ** 3 - ins[p]).max() <= 1e-11
+
+
+def test_live_radix_schedules_of_the_references_generator(co, ref):
+    """What the reference's FFTScheduler actually picks (read back from the plans the executed generator built) against the
+    radix policy restated in oracle_fft.c / used by the product's run-time-scheduled kernel (templateFFT.cpp:3956-3963,
+    4540-4550, 4580-4588): identical for powers of 2, 3, 5 and 7 -- 512 = 8.8.8, 1024 = 8.8.8.2, 4096 = 8.8.8.8 among them --;
+    for mixed lengths the generator merges the 2s into 8s / 4s only when the register count of the other radix allows it
+    (:4540-4550: 768 = 4.4.4.4.3 there, 8.8.4.3 here), a choice that changes rounding, not the transform (the values are
+    compared in test_live_reference_engine_lengths_...).  Lengths beyond one shared-memory line use several uploads."""
+    if ref.set_engine("templatefft") != "templatefft":
+        pytest.skip("libtemplatefft_cpu.so not built")
+    for n in (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 3, 9, 27, 81, 243, 2187, 5, 25, 125, 625, 3125, 7, 49, 343):
+        radices, uploads = ref.engine_schedule(n)
+        assert uploads == 1 and radices == co.radix_schedule(n), (n, radices)
+    for n in (6, 12, 20, 24, 48, 96, 100, 360, 768, 1000, 3000):
+        radices, uploads = ref.engine_schedule(n)
+        assert uploads == 1 and int(np.prod(radices)) == n == int(np.prod(co.radix_schedule(n))) and set(radices) <= {2, 3, 4, 5, 7, 8}
+    assert ref.engine_schedule(768)[0] == [4, 4, 4, 4, 3] and co.radix_schedule(768) == [8, 8, 4, 3]
+    for n in (6144, 6400, 8192):            # multi-upload (four-step) lengths of the reference: two kernels
+        radices, uploads = ref.engine_schedule(n)
+        assert uploads == 2 and int(np.prod(radices)) == n
+    assert ref.engine_schedule(22) is None and ref.engine_schedule(13) is None
