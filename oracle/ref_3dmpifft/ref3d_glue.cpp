@@ -146,6 +146,8 @@ extern "C" int ref3d_engine_schedule(long long n, int* radices, int max_radices,
 extern "C" int cut_transpose3d(data_t* output, const data_t* input, const int* size, const int* permutation, int elements_per_thread)
 {
     if (output == input || elements_per_thread != 1) return -1;     // fftX only uses the out-of-place, 1-element-per-thread form
+    // (valid_parameters, transpose3d.cpp:352-377, also refuses any dimension < 2, which makes the reference abort when a device owns
+    // a single y row; that restriction is a quirk the product and the oracle do not reproduce -- SURVEY A.4 -- and is left out)
     const int d2 = permutation[0] == 0 ? 1 : permutation[0];
     dim3 block(TILE_SIZE, TILE_SIZE / elements_per_thread, 1), grid;
     grid.x = (size[0] + TILE_SIZE - 1) / TILE_SIZE;
