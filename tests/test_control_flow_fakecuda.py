@@ -103,6 +103,37 @@ WORKER = textwrap.dedent(r'''
     plan.execute_host(hin, hout); plan.execute_host_async(hin, hout); plan.synchronize(); plan.destroy()
     for p_ in (buf,): L.dfft_free_local(p_, dfft.ALLOC_DEV)
     for p_ in (hin, hout): L.dfft_free_local(p_, dfft.ALLOC_CPU)
+    # what bench.py's e2e leg does at N > 1: TWO collective plans per device, driven alternately through the host-buffer entry
+    # points (step i's D2H overlaps step i+1's H2D) -- 2 and 8 device-threads
+    def two_plans_in_flight(P, n):
+        comm = dfft.LocalComm(P)
+        errs = []
+        def worker(p):
+            try:
+                mc = dfft.getMaxDataCount(n, n, n, P, p == P - 1)
+                bufs = [dfft.fft_mpi_alloc_local_memory(mc, dfft.ALLOC_DEV) for _ in range(4)]
+                host = [dfft.fft_mpi_alloc_local_memory(mc, dfft.ALLOC_CPU) for _ in range(4)]
+                plans = [dfft.fft_mpi_plan_dft_c2c_3d(n, n, n, bufs[2 * k], bufs[2 * k + 1], comm, p, P, dfft.FORWARD, dfft.DOUBLE, dfft.EXCHANGE_P2P) for k in range(2)]
+                for step in range(6):
+                    k = step % 2
+                    if step >= 2:
+                        plans[k].synchronize()
+                    plans[k].execute_host_async(host[2 * k], host[2 * k + 1])
+                for pl in plans:
+                    pl.synchronize()
+                for pl in plans:
+                    pl.destroy()
+                for b in bufs: L.dfft_free_local(b, dfft.ALLOC_DEV)
+                for b in host: L.dfft_free_local(b, dfft.ALLOC_CPU)
+            except Exception:
+                import traceback
+                errs.append(traceback.format_exc())
+        th = [threading.Thread(target=worker, args=(p,)) for p in range(P)]
+        [t.start() for t in th]; [t.join() for t in th]
+        comm.destroy()
+        assert not errs, "\n".join(errs)
+    two_plans_in_flight(2, 64)
+    two_plans_in_flight(8, 64)
     data = dfft.fft_mpi_alloc_local_memory(4096 * 4, dfft.ALLOC_DEV)
     dfft.fft_lines(data, 4096, 1, 4, 4, 4096, 4 * 4096, dfft.FORWARD)
     lp = dfft.LinesPlan(two_d=(64, 32, 2)); lp.execute(data, dfft.FORWARD); lp.execute(data, dfft.BACKWARD); lp.synchronize(); lp.destroy()
