@@ -315,3 +315,24 @@ def test_live_radix_schedules_of_the_references_generator(co, ref):
         radices, uploads = ref.engine_schedule(n)
         assert uploads == 2 and int(np.prod(radices)) == n
     assert ref.engine_schedule(22) is None and ref.engine_schedule(13) is None
+
+
+@pytest.mark.parametrize("P,n0,n1,n2,flags", [(4, 8, 12, 64, dfft.EXCHANGE_P2P), (2, 64, 64, 64, dfft.EXCHANGE_P2P), (3, 10, 9, 128, dfft.EXCHANGE_P2P),
+                                              (4, 8, 8, 64, dfft.EXCHANGE_NCCL), (8, 16, 16, 64, dfft.EXCHANGE_P2P)])
+def test_live_pipelined_schedules_of_the_product_vs_the_executed_reference(ref, P, n0, n1, n2, flags):
+    """The z-part pipelines (kernel chain for the cube, two streams otherwise, P2P and NCCL, forward and backward): the product's
+    recorded schedule, interpreted on the CPU, gives the slabs the reference's executed code gives."""
+    from test_dry_run import simulate
+    ref.set_engine("templatefft")
+    g = SlabGeometry(n0, n1, n2, P)
+    rng = np.random.default_rng(P * 100 + n2)
+    A = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    scale = np.abs(np.fft.fftn(A)).max()
+    for direction in (FORWARD, BACKWARD):
+        ins = _inputs(g, A, direction)
+        outs, _, _ = ref.execute(g, ins, direction)
+        got, names, _ = simulate(n0, n1, n2, P, direction, ins, flags | dfft.FORCE_PIPELINE)
+        assert len(names[0]) > 4, names[0]          # really cut into parts
+        for p in range(P):
+            n = g.out_count(p) if direction == FORWARD else g.in_count(p)
+            assert np.abs(got[p][:n] - outs[p][:n]).max() <= 1e-13 * np.log2(A.size) * scale, (direction, p)
